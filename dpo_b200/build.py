@@ -1,0 +1,66 @@
+"""In-tree build of the sm_100a shared library (libdpgo_b200.so) with nvcc.
+
+The built .so lives next to the sources (dpo_b200/lib/), is git-ignored, and travels to the GPU
+box with the repo snapshot.  nvcc cross-compiles for sm_100a without a GPU.
+"""
+from __future__ import annotations
+
+import os
+import subprocess
+import sys
+from concurrent.futures import ThreadPoolExecutor
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+LIBDIR = os.path.join(HERE, "lib")
+LIB = os.path.join(LIBDIR, "libdpgo_b200.so")
+SOURCES = ["dpgo_kernels.cu", "dense_inverse.cu", "dpgo_capi.cu"]
+HEADERS = ["dpgo_device.cuh", "dpgo_kernels.cuh", os.path.join("..", "..", "include", "dpgo_b200.h")]
+NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+         "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "-Xptxas", "-v"]
+
+
+def _mtime(path: str) -> float:
+    return os.path.getmtime(path) if os.path.exists(path) else 0.0
+
+
+def needs_build() -> bool:
+    newest = max(_mtime(os.path.join(CSRC, f)) for f in SOURCES + HEADERS)
+    return _mtime(LIB) < newest
+
+
+def build_library(force: bool = False, verbose: bool = False) -> str:
+    if not force and not needs_build():
+        return LIB
+    os.makedirs(LIBDIR, exist_ok=True)
+    objdir = os.path.join(LIBDIR, "obj")
+    os.makedirs(objdir, exist_ok=True)
+    hdr_time = max(_mtime(os.path.join(CSRC, h)) for h in HEADERS)
+
+    def compile_one(src: str) -> str:
+        obj = os.path.join(objdir, src.replace(".cu", ".o"))
+        if not force and _mtime(obj) >= max(_mtime(os.path.join(CSRC, src)), hdr_time):
+            return obj
+        cmd = [NVCC] + FLAGS + ["-c", os.path.join(CSRC, src), "-o", obj]
+        res = subprocess.run(cmd, capture_output=True, text=True)
+        log = os.path.join(objdir, src + ".ptxas.log")
+        with open(log, "w") as fh:
+            fh.write(res.stdout + res.stderr)
+        if res.returncode != 0:
+            raise RuntimeError(f"nvcc failed for {src}:\n{res.stdout}\n{res.stderr}")
+        if verbose:
+            print(res.stderr, file=sys.stderr)
+        return obj
+
+    with ThreadPoolExecutor(max_workers=len(SOURCES)) as ex:
+        objs = list(ex.map(compile_one, SOURCES))
+    cmd = [NVCC, "-shared", "-o", LIB] + objs + ["-gencode", "arch=compute_100a,code=sm_100a", "-cudart", "static"]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if res.returncode != 0:
+        raise RuntimeError(f"link failed:\n{res.stdout}\n{res.stderr}")
+    return LIB
+
+
+if __name__ == "__main__":
+    print(build_library(force="--force" in sys.argv, verbose=True))

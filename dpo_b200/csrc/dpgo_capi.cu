@@ -1,0 +1,801 @@
+// dpgo_capi.cu -- implementation of the C ABI in include/dpgo_b200.h (host side of the library:
+// handle management, CSR -> block-CSR conversion, preconditioner setup, H2D/D2H staging, launches).
+// No CPU compute fallback exists here: every numeric entry point runs the sm_100a kernels.
+#include <cuda_runtime.h>
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <numeric>
+#include <string>
+#include <vector>
+
+#include "dpgo_kernels.cuh"
+
+namespace {
+
+thread_local std::string g_last_error;
+
+int fail(int code, const std::string &msg) {
+  g_last_error = msg;
+  return code;
+}
+
+#define DPGO_CUDA(call)                                                                           \
+  do {                                                                                            \
+    cudaError_t _e = (call);                                                                      \
+    if (_e != cudaSuccess)                                                                        \
+      return fail(DPGO_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(_e));             \
+  } while (0)
+
+#define DPGO_REQUIRE(cond, code, msg) \
+  do {                                \
+    if (!(cond)) return fail(code, msg); \
+  } while (0)
+
+template <class T> void free_dev(T *&p) {
+  if (p) cudaFree(p);
+  p = nullptr;
+}
+
+}  // namespace
+
+struct dpgo_problem {
+  int n = 0, d = 0, r = 0, dh = 0, N = 0, ts = 0;
+  int device = 0, sms = 0, grid = 0, max_grid = 0;
+  cudaStream_t own_stream = nullptr, stream = nullptr;
+  // Q in block-CSR
+  int64_t nb = 0;
+  bool have_Q = false;
+  unsigned precond_mask = 0;
+  int *d_rowptr = nullptr, *d_bcol = nullptr, *d_cta_rows = nullptr;
+  double *d_bval = nullptr, *d_dinv = nullptr, *d_pinv = nullptr;
+  // vectors
+  double *d_G = nullptr;
+  double *d_vec[dpgo::V_COUNT] = {};
+  double *d_S[2] = {nullptr, nullptr};
+  double *d_partials = nullptr;
+  unsigned *d_bar = nullptr;     // [0] arrival counter, [1] epoch
+  dpgo_opt_result_t *d_result = nullptr;
+  dpgo_opt_result_t *h_result = nullptr;   // pinned
+  bool async_pending = false;
+  std::chrono::high_resolution_clock::time_point async_t0;
+  // exchange
+  int num_public = 0;
+  int *d_public = nullptr;
+  int num_edges = 0, num_shared_poses = 0;
+  int *d_pose_ids = nullptr, *d_pose_ptr = nullptr, *d_edge_slot = nullptr, *d_edge_out = nullptr;
+  double *d_edge_T = nullptr, *d_edge_om = nullptr;
+
+  size_t vec_bytes() const { return sizeof(double) * (size_t)r * (size_t)N; }
+};
+
+namespace {
+
+void fill_kparams(const dpgo_problem *p, dpgo::KParams &kp, int op, const dpgo_opt_params_t &prm) {
+  kp.n = p->n;
+  kp.N = p->N;
+  kp.grid = p->grid;
+  kp.op = op;
+  kp.rowptr = p->d_rowptr;
+  kp.bcol = p->d_bcol;
+  kp.bval = p->d_bval;
+  kp.dinv = p->d_dinv;
+  kp.pinv = p->d_pinv;
+  kp.cta_rows = p->d_cta_rows;
+  kp.G = p->d_G;
+  for (int i = 0; i < dpgo::V_COUNT; ++i) kp.v[i] = p->d_vec[i];
+  kp.S[0] = p->d_S[0];
+  kp.S[1] = p->d_S[1];
+  kp.partials = p->d_partials;
+  kp.bar_counter = p->d_bar;
+  kp.bar_epoch = p->d_bar + 1;
+  kp.prm = prm;
+  kp.result = p->d_result;
+}
+
+int check_precond(const dpgo_problem *p, int precond) {
+  if (precond < 0 || precond > 2) return fail(DPGO_ERR_INVALID_ARG, "unknown preconditioner id");
+  if (precond == DPGO_PRECOND_BLOCK_JACOBI && !p->d_dinv)
+    return fail(DPGO_ERR_STATE, "block-Jacobi preconditioner was not prepared by set_Q (precond_mask)");
+  if (precond == DPGO_PRECOND_DENSE_EXACT && !p->d_pinv)
+    return fail(DPGO_ERR_STATE, "dense exact preconditioner was not prepared by set_Q (precond_mask)");
+  return DPGO_OK;
+}
+
+int run_op(dpgo_problem *p, int op, const dpgo_opt_params_t &prm) {
+  DPGO_REQUIRE(p->have_Q, DPGO_ERR_STATE, "set_Q has not been called");
+  dpgo::KParams kp;
+  fill_kparams(p, kp, op, prm);
+  DPGO_CUDA(dpgo::launch_optimize(p->r, p->dh, kp, p->stream));
+  return DPGO_OK;
+}
+
+// ---- host-side block assembly ---------------------------------------------------------------
+struct BlockTriplet {
+  int brow, bcol;      // Q sub-block at rows dh*brow.., cols dh*bcol..
+  double v[16];        // padded 4x4, v[k*4+c] = Q[dh*brow+k, dh*bcol+c]
+};
+
+int build_from_triplets(dpgo_problem *p, std::vector<BlockTriplet> &trip, unsigned precond_mask) {
+  const int n = p->n, dh = p->dh;
+  // sort by (output tile = bcol, neighbour tile = brow); stable so duplicate summation order is fixed
+  std::vector<int64_t> order(trip.size());
+  std::iota(order.begin(), order.end(), 0);
+  std::stable_sort(order.begin(), order.end(), [&](int64_t x, int64_t y) {
+    if (trip[x].bcol != trip[y].bcol) return trip[x].bcol < trip[y].bcol;
+    return trip[x].brow < trip[y].brow;
+  });
+  std::vector<int> rowptr(n + 1, 0), bcol;
+  std::vector<double> bval;
+  bcol.reserve(trip.size());
+  bval.reserve(trip.size() * 16);
+  int last_j = -1, last_i = -1;
+  for (int64_t o : order) {
+    const BlockTriplet &t = trip[o];
+    if (t.bcol == last_j && t.brow == last_i) {
+      double *dst = &bval[bval.size() - 16];
+      for (int e = 0; e < 16; ++e) dst[e] += t.v[e];
+    } else {
+      bcol.push_back(t.brow);
+      bval.insert(bval.end(), t.v, t.v + 16);
+      rowptr[t.bcol + 1]++;
+      last_j = t.bcol;
+      last_i = t.brow;
+    }
+  }
+  for (int j = 0; j < n; ++j) rowptr[j + 1] += rowptr[j];
+  const int64_t nb = (int64_t)bcol.size();
+
+  // block-Jacobi inverse blocks (Q_jj + 0.1 I)^-1, stored [k][c] padded
+  std::vector<double> dinv;
+  if (precond_mask & (1u << DPGO_PRECOND_BLOCK_JACOBI)) {
+    dinv.assign((size_t)n * 16, 0.0);
+    for (int j = 0; j < n; ++j) {
+      double A[4][8];
+      for (int k = 0; k < 4; ++k)
+        for (int c = 0; c < 8; ++c) A[k][c] = (c >= 4 && c - 4 == k) ? 1.0 : 0.0;
+      for (int k = 0; k < dh; ++k) A[k][k] = 0.1;
+      for (int k = dh; k < 4; ++k) A[k][k] = 1.0;
+      for (int b = rowptr[j]; b < rowptr[j + 1]; ++b)
+        if (bcol[b] == j)
+          for (int k = 0; k < dh; ++k)
+            for (int c = 0; c < dh; ++c) A[k][c] += bval[(size_t)b * 16 + k * 4 + c];
+      for (int k = 0; k < 4; ++k) {          // Gauss-Jordan, SPD so no pivoting
+        const double inv = 1.0 / A[k][k];
+        for (int c = 0; c < 8; ++c) A[k][c] *= inv;
+        for (int i = 0; i < 4; ++i)
+          if (i != k) {
+            const double f = A[i][k];
+            for (int c = 0; c < 8; ++c) A[i][c] -= f * A[k][c];
+          }
+      }
+      for (int k = 0; k < dh; ++k)
+        for (int c = 0; c < dh; ++c) dinv[(size_t)j * 16 + k * 4 + c] = A[k][4 + c];
+    }
+  }
+
+  // persistent-kernel grid and balanced row partition
+  const int sg = (p->r > 4) ? 32 : ((p->r > 2) ? 16 : 8);
+  const int rows_per_pass = (dpgo::OPT_THREADS / 32) * (32 / sg);
+  int grid = p->max_grid;
+  const bool dense = (precond_mask & (1u << DPGO_PRECOND_DENSE_EXACT)) != 0;
+  if (!dense) grid = std::max(1, std::min(grid, (n + rows_per_pass - 1) / rows_per_pass));
+  std::vector<int> cta_rows(grid + 1, 0);
+  {
+    // cost model: blocks + constant epilogue weight per row
+    const double wrow = 4.0;
+    double total = 0.0;
+    for (int j = 0; j < n; ++j) total += (rowptr[j + 1] - rowptr[j]) + wrow;
+    double accw = 0.0;
+    int ci = 1;
+    for (int j = 0; j < n; ++j) {
+      accw += (rowptr[j + 1] - rowptr[j]) + wrow;
+      while (ci < grid && accw >= total * ci / grid) cta_rows[ci++] = j + 1;
+    }
+    while (ci <= grid) cta_rows[ci++] = n;
+  }
+
+  // upload
+  cudaSetDevice(p->device);
+  free_dev(p->d_rowptr); free_dev(p->d_bcol); free_dev(p->d_bval); free_dev(p->d_dinv); free_dev(p->d_pinv);
+  free_dev(p->d_cta_rows); free_dev(p->d_partials);
+  p->have_Q = false;
+  DPGO_CUDA(cudaMalloc(&p->d_rowptr, sizeof(int) * (n + 1)));
+  DPGO_CUDA(cudaMalloc(&p->d_bcol, sizeof(int) * std::max<int64_t>(nb, 1)));
+  DPGO_CUDA(cudaMalloc(&p->d_bval, sizeof(double) * 16 * std::max<int64_t>(nb, 1)));
+  DPGO_CUDA(cudaMalloc(&p->d_cta_rows, sizeof(int) * (grid + 1)));
+  DPGO_CUDA(cudaMalloc(&p->d_partials, sizeof(double) * 2 * grid * dpgo::NRED));
+  DPGO_CUDA(cudaMemcpyAsync(p->d_rowptr, rowptr.data(), sizeof(int) * (n + 1), cudaMemcpyHostToDevice, p->stream));
+  if (nb) {
+    DPGO_CUDA(cudaMemcpyAsync(p->d_bcol, bcol.data(), sizeof(int) * nb, cudaMemcpyHostToDevice, p->stream));
+    DPGO_CUDA(cudaMemcpyAsync(p->d_bval, bval.data(), sizeof(double) * 16 * nb, cudaMemcpyHostToDevice, p->stream));
+  }
+  DPGO_CUDA(cudaMemcpyAsync(p->d_cta_rows, cta_rows.data(), sizeof(int) * (grid + 1), cudaMemcpyHostToDevice, p->stream));
+  DPGO_CUDA(cudaMemsetAsync(p->d_partials, 0, sizeof(double) * 2 * grid * dpgo::NRED, p->stream));
+  if (!dinv.empty()) {
+    DPGO_CUDA(cudaMalloc(&p->d_dinv, sizeof(double) * dinv.size()));
+    DPGO_CUDA(cudaMemcpyAsync(p->d_dinv, dinv.data(), sizeof(double) * dinv.size(), cudaMemcpyHostToDevice, p->stream));
+  }
+  DPGO_CUDA(cudaStreamSynchronize(p->stream));
+  p->nb = nb;
+  p->grid = grid;
+  p->precond_mask = precond_mask;
+
+  if (dense) {
+    const size_t N = (size_t)p->N;
+    if (N * N * sizeof(double) > (size_t)48 << 30)
+      return fail(DPGO_ERR_UNSUPPORTED, "dense exact preconditioner limited to N^2*8 <= 48 GiB; use block-Jacobi");
+    DPGO_CUDA(cudaMalloc(&p->d_pinv, N * N * sizeof(double)));
+    DPGO_CUDA(cudaMemsetAsync(p->d_pinv, 0, N * N * sizeof(double), p->stream));
+    // scatter Q + 0.1 I into the dense buffer on the host side of a staging copy would cost N^2 of
+    // PCIe traffic; instead scatter block rows with small strided copies: one cudaMemcpy2DAsync per
+    // block would be too many calls, so build per-column strips on the host for only the nonzeros.
+    // Simple and bounded: upload (row, col, val) scalar triplets and scatter with a kernel.
+    std::vector<int> trow, tcol;
+    std::vector<double> tval;
+    trow.reserve((size_t)nb * dh * dh + N);
+    tcol.reserve((size_t)nb * dh * dh + N);
+    tval.reserve((size_t)nb * dh * dh + N);
+    for (int j = 0; j < n; ++j)
+      for (int b = rowptr[j]; b < rowptr[j + 1]; ++b) {
+        const int i = bcol[b];
+        for (int k = 0; k < dh; ++k)
+          for (int c = 0; c < dh; ++c) {
+            double v = bval[(size_t)b * 16 + k * 4 + c];
+            if (i == j && k == c) v += 0.1;
+            trow.push_back(dh * i + k);
+            tcol.push_back(dh * j + c);
+            tval.push_back(v);
+          }
+      }
+    // poses with no diagonal block at all (isolated) still need the 0.1 shift
+    {
+      std::vector<char> has_diag(n, 0);
+      for (int j = 0; j < n; ++j)
+        for (int b = rowptr[j]; b < rowptr[j + 1]; ++b)
+          if (bcol[b] == j) has_diag[j] = 1;
+      for (int j = 0; j < n; ++j)
+        if (!has_diag[j])
+          for (int k = 0; k < dh; ++k) { trow.push_back(dh * j + k); tcol.push_back(dh * j + k); tval.push_back(0.1); }
+    }
+    int *d_tr = nullptr, *d_tc = nullptr;
+    double *d_tv = nullptr;
+    const size_t nt = tval.size();
+    DPGO_CUDA(cudaMalloc(&d_tr, sizeof(int) * nt));
+    DPGO_CUDA(cudaMalloc(&d_tc, sizeof(int) * nt));
+    DPGO_CUDA(cudaMalloc(&d_tv, sizeof(double) * nt));
+    DPGO_CUDA(cudaMemcpyAsync(d_tr, trow.data(), sizeof(int) * nt, cudaMemcpyHostToDevice, p->stream));
+    DPGO_CUDA(cudaMemcpyAsync(d_tc, tcol.data(), sizeof(int) * nt, cudaMemcpyHostToDevice, p->stream));
+    DPGO_CUDA(cudaMemcpyAsync(d_tv, tval.data(), sizeof(double) * nt, cudaMemcpyHostToDevice, p->stream));
+    cudaError_t e = dpgo::launch_scatter_dense(d_tr, d_tc, d_tv, (int64_t)nt, p->d_pinv, p->N, p->stream);
+    if (e == cudaSuccess) e = dpgo::dense_spd_inverse(p->d_pinv, p->N, p->stream);
+    cudaFree(d_tr); cudaFree(d_tc); cudaFree(d_tv);
+    if (e != cudaSuccess) return fail(DPGO_ERR_CUDA, std::string("dense preconditioner setup: ") + cudaGetErrorString(e));
+  }
+  p->have_Q = true;
+  return DPGO_OK;
+}
+
+int upload_vec(dpgo_problem *p, int id, const double *host) {
+  DPGO_CUDA(cudaMemcpyAsync(p->d_vec[id], host, p->vec_bytes(), cudaMemcpyHostToDevice, p->stream));
+  return DPGO_OK;
+}
+int download_vec(dpgo_problem *p, int id, double *host) {
+  DPGO_CUDA(cudaMemcpyAsync(host, p->d_vec[id], p->vec_bytes(), cudaMemcpyDeviceToHost, p->stream));
+  return DPGO_OK;
+}
+int fetch_result(dpgo_problem *p) {
+  DPGO_CUDA(cudaMemcpyAsync(p->h_result, p->d_result, sizeof(dpgo_opt_result_t), cudaMemcpyDeviceToHost, p->stream));
+  DPGO_CUDA(cudaStreamSynchronize(p->stream));
+  return DPGO_OK;
+}
+
+#define DPGO_CHECK_HANDLE(p)                                                         \
+  do {                                                                               \
+    if (!(p)) return fail(DPGO_ERR_INVALID_ARG, "null problem handle");              \
+    cudaError_t _e = cudaSetDevice((p)->device);                                     \
+    if (_e != cudaSuccess) return fail(DPGO_ERR_CUDA, cudaGetErrorString(_e));       \
+  } while (0)
+#define DPGO_TRY(expr)            \
+  do {                            \
+    int _s = (expr);              \
+    if (_s != DPGO_OK) return _s; \
+  } while (0)
+
+}  // namespace
+
+extern "C" {
+
+int dpgo_abi_version(void) { return DPGO_B200_ABI_VERSION; }
+const char *dpgo_last_error(void) { return g_last_error.c_str(); }
+
+int dpgo_device_count(int *count) {
+  DPGO_REQUIRE(count, DPGO_ERR_INVALID_ARG, "null count");
+  int c = 0;
+  cudaError_t e = cudaGetDeviceCount(&c);
+  if (e != cudaSuccess) {
+    *count = 0;
+    return fail(DPGO_ERR_NO_DEVICE, std::string("cudaGetDeviceCount: ") + cudaGetErrorString(e));
+  }
+  *count = c;
+  return DPGO_OK;
+}
+
+void dpgo_opt_params_default(dpgo_opt_params_t *p) {
+  if (!p) return;
+  p->algorithm = DPGO_ALG_RTR;        // ref: src/QuadraticOptimizer.cpp:22-28
+  p->tr_iterations = 1;
+  p->tr_max_inner = 50;
+  p->precond = DPGO_PRECOND_DENSE_EXACT;
+  p->rgd_stepsize = 1e-3;
+  p->tr_tolerance = 1e-2;
+  p->tr_initial_radius = 1e1;
+}
+
+int dpgo_problem_create(int n, int d, int r, int device, dpgo_problem_t **out) {
+  DPGO_REQUIRE(out, DPGO_ERR_INVALID_ARG, "null output handle");
+  *out = nullptr;
+  DPGO_REQUIRE(n >= 1, DPGO_ERR_INVALID_ARG, "n must be >= 1");
+  DPGO_REQUIRE(d == 2 || d == 3, DPGO_ERR_UNSUPPORTED, "d must be 2 or 3");
+  DPGO_REQUIRE(r >= d, DPGO_ERR_INVALID_ARG, "r must be >= d (ref: assert(r >= d), src/QuadraticProblem.cpp:19)");
+  DPGO_REQUIRE((d == 3 && r <= 5) || (d == 2 && (r <= 3 || r == 5)), DPGO_ERR_UNSUPPORTED,
+               "unsupported rank (compiled instantiations: d=3: r in 3..5; d=2: r in {2,3,5})");
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count == 0)
+    return fail(DPGO_ERR_NO_DEVICE, "no CUDA device available: the B200 path has no CPU fallback");
+  DPGO_REQUIRE(device >= 0 && device < count, DPGO_ERR_NO_DEVICE, "device index out of range");
+  DPGO_CUDA(cudaSetDevice(device));
+  dpgo_problem *p = new (std::nothrow) dpgo_problem();
+  if (!p) return fail(DPGO_ERR_ALLOC, "host allocation failed");
+  p->n = n; p->d = d; p->r = r; p->dh = d + 1; p->N = (d + 1) * n; p->ts = r * (d + 1);
+  p->device = device;
+  auto bail = [&](int code, const std::string &m) { dpgo_problem_destroy(p); return fail(code, m); };
+  if (cudaDeviceGetAttribute(&p->sms, cudaDevAttrMultiProcessorCount, device) != cudaSuccess)
+    return bail(DPGO_ERR_CUDA, "cudaDeviceGetAttribute failed");
+  if (cudaStreamCreateWithFlags(&p->own_stream, cudaStreamNonBlocking) != cudaSuccess)
+    return bail(DPGO_ERR_CUDA, "cudaStreamCreate failed");
+  p->stream = p->own_stream;
+  p->max_grid = dpgo::optimize_max_grid(r, d + 1, device);
+  if (p->max_grid <= 0) return bail(DPGO_ERR_CUDA, "persistent kernel cannot be made resident on this device");
+  const size_t vb = p->vec_bytes();
+  for (int i = 0; i < dpgo::V_COUNT; ++i) {
+    if (cudaMalloc(&p->d_vec[i], vb) != cudaSuccess) return bail(DPGO_ERR_ALLOC, "device allocation failed (vectors)");
+    cudaMemsetAsync(p->d_vec[i], 0, vb, p->stream);
+  }
+  if (cudaMalloc(&p->d_G, vb) != cudaSuccess) return bail(DPGO_ERR_ALLOC, "device allocation failed (G)");
+  cudaMemsetAsync(p->d_G, 0, vb, p->stream);
+  for (int i = 0; i < 2; ++i) {
+    if (cudaMalloc(&p->d_S[i], sizeof(double) * 9 * (size_t)n) != cudaSuccess) return bail(DPGO_ERR_ALLOC, "device allocation failed (S)");
+    cudaMemsetAsync(p->d_S[i], 0, sizeof(double) * 9 * (size_t)n, p->stream);
+  }
+  if (cudaMalloc(&p->d_bar, 2 * sizeof(unsigned)) != cudaSuccess) return bail(DPGO_ERR_ALLOC, "device allocation failed");
+  cudaMemsetAsync(p->d_bar, 0, 2 * sizeof(unsigned), p->stream);
+  if (cudaMalloc(&p->d_result, sizeof(dpgo_opt_result_t)) != cudaSuccess) return bail(DPGO_ERR_ALLOC, "device allocation failed");
+  if (cudaMallocHost(&p->h_result, sizeof(dpgo_opt_result_t)) != cudaSuccess) return bail(DPGO_ERR_ALLOC, "pinned allocation failed");
+  if (cudaStreamSynchronize(p->stream) != cudaSuccess) return bail(DPGO_ERR_CUDA, "device initialisation failed");
+  // empty Q (ref: ctor calls setQ(SparseMatrix(N,N)), src/QuadraticProblem.cpp:23)
+  std::vector<BlockTriplet> none;
+  int s = build_from_triplets(p, none, 1u << DPGO_PRECOND_BLOCK_JACOBI);
+  if (s != DPGO_OK) { std::string m = g_last_error; dpgo_problem_destroy(p); return fail(s, m); }
+  *out = p;
+  return DPGO_OK;
+}
+
+int dpgo_problem_destroy(dpgo_problem_t *p) {
+  if (!p) return DPGO_OK;
+  cudaSetDevice(p->device);
+  if (p->stream) cudaStreamSynchronize(p->stream);
+  free_dev(p->d_rowptr); free_dev(p->d_bcol); free_dev(p->d_cta_rows); free_dev(p->d_bval);
+  free_dev(p->d_dinv); free_dev(p->d_pinv); free_dev(p->d_G);
+  for (int i = 0; i < dpgo::V_COUNT; ++i) free_dev(p->d_vec[i]);
+  free_dev(p->d_S[0]); free_dev(p->d_S[1]); free_dev(p->d_partials); free_dev(p->d_bar); free_dev(p->d_result);
+  free_dev(p->d_public); free_dev(p->d_pose_ids); free_dev(p->d_pose_ptr); free_dev(p->d_edge_slot);
+  free_dev(p->d_edge_out); free_dev(p->d_edge_T); free_dev(p->d_edge_om);
+  if (p->h_result) cudaFreeHost(p->h_result);
+  if (p->own_stream) cudaStreamDestroy(p->own_stream);
+  delete p;
+  return DPGO_OK;
+}
+
+int dpgo_problem_set_stream(dpgo_problem_t *p, void *cuda_stream) {
+  DPGO_CHECK_HANDLE(p);
+  DPGO_CUDA(cudaStreamSynchronize(p->stream));
+  p->stream = cuda_stream ? (cudaStream_t)cuda_stream : p->own_stream;
+  return DPGO_OK;
+}
+
+int dpgo_problem_sync(dpgo_problem_t *p) {
+  DPGO_CHECK_HANDLE(p);
+  DPGO_CUDA(cudaStreamSynchronize(p->stream));
+  return DPGO_OK;
+}
+
+int dpgo_problem_dims(const dpgo_problem_t *p, int *n, int *d, int *r, int64_t *num_blocks) {
+  DPGO_REQUIRE(p, DPGO_ERR_INVALID_ARG, "null problem handle");
+  if (n) *n = p->n;
+  if (d) *d = p->d;
+  if (r) *r = p->r;
+  if (num_blocks) *num_blocks = p->nb;
+  return DPGO_OK;
+}
+
+int dpgo_problem_set_Q_csr(dpgo_problem_t *p, int nrows, const int32_t *rowptr, const int32_t *colind,
+                           const double *values, unsigned precond_mask) {
+  DPGO_CHECK_HANDLE(p);
+  DPGO_REQUIRE(nrows == p->N, DPGO_ERR_INVALID_ARG, "Q must be (d+1)n x (d+1)n");
+  DPGO_REQUIRE(rowptr && (rowptr[nrows] == 0 || (colind && values)), DPGO_ERR_INVALID_ARG, "null CSR arrays");
+  const int dh = p->dh;
+  std::vector<BlockTriplet> trip;
+  trip.reserve((size_t)rowptr[nrows] / (dh * dh) + 16);
+  for (int ib = 0; ib < p->n; ++ib) {
+    const size_t first = trip.size();
+    for (int k = 0; k < dh; ++k) {
+      const int rr = ib * dh + k;
+      for (int q = rowptr[rr]; q < rowptr[rr + 1]; ++q) {
+        const int cc = colind[q];
+        if (cc < 0 || cc >= p->N) return fail(DPGO_ERR_INVALID_ARG, "column index out of range");
+        const int jb = cc / dh, c = cc - jb * dh;
+        size_t t = first;
+        for (; t < trip.size(); ++t)
+          if (trip[t].bcol == jb) break;
+        if (t == trip.size()) {
+          BlockTriplet bt;
+          bt.brow = ib;
+          bt.bcol = jb;
+          std::memset(bt.v, 0, sizeof(bt.v));
+          trip.push_back(bt);
+        }
+        trip[t].v[k * 4 + c] += values[q];
+      }
+    }
+  }
+  return build_from_triplets(p, trip, precond_mask);
+}
+
+int dpgo_problem_set_Q_blocks(dpgo_problem_t *p, int64_t nb, const int32_t *brow, const int32_t *bcol,
+                              const double *blocks, unsigned precond_mask) {
+  DPGO_CHECK_HANDLE(p);
+  DPGO_REQUIRE(nb >= 0 && (nb == 0 || (brow && bcol && blocks)), DPGO_ERR_INVALID_ARG, "null block arrays");
+  const int dh = p->dh;
+  std::vector<BlockTriplet> trip((size_t)nb);
+  for (int64_t q = 0; q < nb; ++q) {
+    if (brow[q] < 0 || brow[q] >= p->n || bcol[q] < 0 || bcol[q] >= p->n)
+      return fail(DPGO_ERR_INVALID_ARG, "block index out of range");
+    trip[q].brow = brow[q];
+    trip[q].bcol = bcol[q];
+    std::memset(trip[q].v, 0, sizeof(trip[q].v));
+    for (int k = 0; k < dh; ++k)
+      for (int c = 0; c < dh; ++c) trip[q].v[k * 4 + c] = blocks[(size_t)q * dh * dh + k * dh + c];
+  }
+  return build_from_triplets(p, trip, precond_mask);
+}
+
+int dpgo_problem_set_G_dense(dpgo_problem_t *p, const double *G_host) {
+  DPGO_CHECK_HANDLE(p);
+  if (!G_host) {
+    DPGO_CUDA(cudaMemsetAsync(p->d_G, 0, p->vec_bytes(), p->stream));
+  } else {
+    DPGO_CUDA(cudaMemcpyAsync(p->d_G, G_host, p->vec_bytes(), cudaMemcpyHostToDevice, p->stream));
+  }
+  DPGO_CUDA(cudaStreamSynchronize(p->stream));
+  return DPGO_OK;
+}
+
+int dpgo_problem_set_G_csr(dpgo_problem_t *p, const int32_t *rowptr, const int32_t *colind, const double *values) {
+  DPGO_CHECK_HANDLE(p);
+  if (!rowptr) return dpgo_problem_set_G_dense(p, nullptr);
+  std::vector<double> G((size_t)p->r * p->N, 0.0);
+  for (int a = 0; a < p->r; ++a)
+    for (int q = rowptr[a]; q < rowptr[a + 1]; ++q) {
+      if (colind[q] < 0 || colind[q] >= p->N) return fail(DPGO_ERR_INVALID_ARG, "G column index out of range");
+      G[(size_t)colind[q] * p->r + a] += values[q];
+    }
+  return dpgo_problem_set_G_dense(p, G.data());
+}
+
+// ---- evaluation ---------------------------------------------------------------------------------
+static int eval_at(dpgo_problem_t *p, const double *X_host) {
+  DPGO_REQUIRE(X_host, DPGO_ERR_INVALID_ARG, "null X");
+  DPGO_TRY(upload_vec(p, dpgo::V_X0, X_host));
+  dpgo_opt_params_t prm;
+  dpgo_opt_params_default(&prm);
+  prm.precond = DPGO_PRECOND_NONE;
+  DPGO_TRY(run_op(p, dpgo::OP_EVAL, prm));
+  return DPGO_OK;
+}
+
+int dpgo_problem_f(dpgo_problem_t *p, const double *X_host, double *f_out) {
+  DPGO_CHECK_HANDLE(p);
+  DPGO_REQUIRE(f_out, DPGO_ERR_INVALID_ARG, "null output");
+  DPGO_TRY(eval_at(p, X_host));
+  DPGO_TRY(fetch_result(p));
+  *f_out = p->h_result->f_init;
+  return DPGO_OK;
+}
+
+int dpgo_problem_egrad(dpgo_problem_t *p, const double *X_host, double *out_host) {
+  DPGO_CHECK_HANDLE(p);
+  DPGO_REQUIRE(out_host, DPGO_ERR_INVALID_ARG, "null output");
+  DPGO_TRY(eval_at(p, X_host));
+  DPGO_TRY(download_vec(p, dpgo::V_EG0, out_host));
+  DPGO_CUDA(cudaStreamSynchronize(p->stream));
+  return DPGO_OK;
+}
+
+int dpgo_problem_ehess(dpgo_problem_t *p, const double *V_host, double *out_host) {
+  DPGO_CHECK_HANDLE(p);
+  DPGO_REQUIRE(V_host && out_host, DPGO_ERR_INVALID_ARG, "null argument");
+  DPGO_REQUIRE(p->have_Q, DPGO_ERR_STATE, "set_Q has not been called");
+  DPGO_TRY(upload_vec(p, dpgo::V_AUX, V_host));
+  DPGO_CUDA(dpgo::launch_spmv(p->r, p->dh, p->n, p->d_rowptr, p->d_bcol, p->d_bval, p->d_vec[dpgo::V_AUX], nullptr,
+                              p->d_vec[dpgo::V_HD], p->stream));
+  DPGO_TRY(download_vec(p, dpgo::V_HD, out_host));
+  DPGO_CUDA(cudaStreamSynchronize(p->stream));
+  return DPGO_OK;
+}
+
+int dpgo_problem_rgrad(dpgo_problem_t *p, const double *X_host, double *out_host, double *norm_out) {
+  DPGO_CHECK_HANDLE(p);
+  DPGO_TRY(eval_at(p, X_host));
+  if (out_host) DPGO_TRY(download_vec(p, dpgo::V_RG0, out_host));
+  DPGO_TRY(fetch_result(p));
+  if (norm_out) *norm_out = p->h_result->gradnorm_init;
+  return DPGO_OK;
+}
+
+int dpgo_problem_f_rgradnorm(dpgo_problem_t *p, const double *X_host, double *f_out, double *norm_out) {
+  DPGO_CHECK_HANDLE(p);
+  DPGO_TRY(eval_at(p, X_host));
+  DPGO_TRY(fetch_result(p));
+  if (f_out) *f_out = p->h_result->f_init;
+  if (norm_out) *norm_out = p->h_result->gradnorm_init;
+  return DPGO_OK;
+}
+
+int dpgo_problem_rhess(dpgo_problem_t *p, const double *X_host, const double *V_host, double *out_host) {
+  DPGO_CHECK_HANDLE(p);
+  DPGO_REQUIRE(X_host && V_host && out_host, DPGO_ERR_INVALID_ARG, "null argument");
+  DPGO_TRY(upload_vec(p, dpgo::V_X0, X_host));
+  DPGO_TRY(upload_vec(p, dpgo::V_AUX, V_host));
+  dpgo_opt_params_t prm;
+  dpgo_opt_params_default(&prm);
+  prm.precond = DPGO_PRECOND_NONE;
+  DPGO_TRY(run_op(p, dpgo::OP_RHESS, prm));
+  DPGO_TRY(download_vec(p, dpgo::V_HD, out_host));
+  DPGO_CUDA(cudaStreamSynchronize(p->stream));
+  return DPGO_OK;
+}
+
+int dpgo_problem_precon(dpgo_problem_t *p, int precond, const double *X_host, const double *V_host, double *out_host) {
+  DPGO_CHECK_HANDLE(p);
+  DPGO_REQUIRE(X_host && V_host && out_host, DPGO_ERR_INVALID_ARG, "null argument");
+  DPGO_TRY(check_precond(p, precond));
+  DPGO_TRY(upload_vec(p, dpgo::V_X0, X_host));
+  DPGO_TRY(upload_vec(p, dpgo::V_AUX, V_host));
+  dpgo_opt_params_t prm;
+  dpgo_opt_params_default(&prm);
+  prm.precond = precond;
+  DPGO_TRY(run_op(p, dpgo::OP_PRECON, prm));
+  DPGO_TRY(download_vec(p, dpgo::V_Z, out_host));
+  DPGO_CUDA(cudaStreamSynchronize(p->stream));
+  return DPGO_OK;
+}
+
+int dpgo_manifold_tangent_project(dpgo_problem_t *p, const double *X_host, const double *Z_host, double *out_host) {
+  return dpgo_problem_precon(p, DPGO_PRECOND_NONE, X_host, Z_host, out_host);
+}
+
+int dpgo_manifold_retract(dpgo_problem_t *p, const double *X_host, const double *eta_host, double *out_host) {
+  DPGO_CHECK_HANDLE(p);
+  DPGO_REQUIRE(X_host && eta_host && out_host, DPGO_ERR_INVALID_ARG, "null argument");
+  DPGO_TRY(upload_vec(p, dpgo::V_X0, X_host));
+  DPGO_TRY(upload_vec(p, dpgo::V_AUX, eta_host));
+  dpgo_opt_params_t prm;
+  dpgo_opt_params_default(&prm);
+  prm.precond = DPGO_PRECOND_NONE;
+  DPGO_TRY(run_op(p, dpgo::OP_RETRACT, prm));
+  DPGO_TRY(download_vec(p, dpgo::V_X1, out_host));
+  DPGO_CUDA(cudaStreamSynchronize(p->stream));
+  return DPGO_OK;
+}
+
+int dpgo_manifold_project(dpgo_problem_t *p, const double *M_host, double *out_host) {
+  DPGO_CHECK_HANDLE(p);
+  DPGO_REQUIRE(M_host && out_host, DPGO_ERR_INVALID_ARG, "null argument");
+  DPGO_TRY(upload_vec(p, dpgo::V_AUX, M_host));
+  DPGO_CUDA(dpgo::launch_stiefel_project(p->r, p->dh, p->n, p->d_vec[dpgo::V_AUX], p->d_vec[dpgo::V_T], p->stream));
+  DPGO_TRY(download_vec(p, dpgo::V_T, out_host));
+  DPGO_CUDA(cudaStreamSynchronize(p->stream));
+  return DPGO_OK;
+}
+
+// ---- optimiser -----------------------------------------------------------------------------------
+static int check_params(const dpgo_problem_t *p, const dpgo_opt_params_t *prm) {
+  DPGO_REQUIRE(prm, DPGO_ERR_INVALID_ARG, "null params");
+  DPGO_REQUIRE(prm->algorithm == DPGO_ALG_RTR || prm->algorithm == DPGO_ALG_RGD, DPGO_ERR_INVALID_ARG, "unknown algorithm");
+  DPGO_REQUIRE(prm->tr_iterations >= 1 && prm->tr_max_inner >= 1, DPGO_ERR_INVALID_ARG, "iteration counts must be >= 1");
+  DPGO_REQUIRE(prm->tr_initial_radius > 0 && prm->tr_tolerance >= 0, DPGO_ERR_INVALID_ARG, "bad radius / tolerance");
+  if (prm->algorithm == DPGO_ALG_RTR) DPGO_TRY(check_precond(p, prm->precond));
+  return DPGO_OK;
+}
+
+int dpgo_optimize(dpgo_problem_t *p, const dpgo_opt_params_t *params, const double *X_in_host, double *X_out_host,
+                  dpgo_opt_result_t *result) {
+  DPGO_CHECK_HANDLE(p);
+  DPGO_REQUIRE(X_in_host && X_out_host, DPGO_ERR_INVALID_ARG, "null X");
+  DPGO_TRY(check_params(p, params));
+  const auto t0 = std::chrono::high_resolution_clock::now();
+  DPGO_TRY(upload_vec(p, dpgo::V_X0, X_in_host));
+  DPGO_TRY(run_op(p, dpgo::OP_OPTIMIZE, *params));
+  DPGO_TRY(download_vec(p, dpgo::V_X0, X_out_host));
+  DPGO_TRY(fetch_result(p));
+  const auto t1 = std::chrono::high_resolution_clock::now();
+  p->h_result->elapsed_ms = std::chrono::duration<double, std::milli>(t1 - t0).count();
+  if (result) *result = *p->h_result;
+  return DPGO_OK;
+}
+
+int dpgo_problem_upload_X(dpgo_problem_t *p, const double *X_host) {
+  DPGO_CHECK_HANDLE(p);
+  DPGO_REQUIRE(X_host, DPGO_ERR_INVALID_ARG, "null X");
+  DPGO_TRY(upload_vec(p, dpgo::V_X0, X_host));
+  DPGO_CUDA(cudaStreamSynchronize(p->stream));
+  return DPGO_OK;
+}
+
+int dpgo_problem_download_X(dpgo_problem_t *p, double *X_host) {
+  DPGO_CHECK_HANDLE(p);
+  DPGO_REQUIRE(X_host, DPGO_ERR_INVALID_ARG, "null X");
+  DPGO_TRY(download_vec(p, dpgo::V_X0, X_host));
+  DPGO_CUDA(cudaStreamSynchronize(p->stream));
+  return DPGO_OK;
+}
+
+int dpgo_problem_device_X(dpgo_problem_t *p, double **X_dev) {
+  DPGO_REQUIRE(p && X_dev, DPGO_ERR_INVALID_ARG, "null argument");
+  *X_dev = p->d_vec[dpgo::V_X0];
+  return DPGO_OK;
+}
+
+int dpgo_problem_device_G(dpgo_problem_t *p, double **G_dev) {
+  DPGO_REQUIRE(p && G_dev, DPGO_ERR_INVALID_ARG, "null argument");
+  *G_dev = p->d_G;
+  return DPGO_OK;
+}
+
+int dpgo_optimize_resident_async(dpgo_problem_t *p, const dpgo_opt_params_t *params) {
+  DPGO_CHECK_HANDLE(p);
+  DPGO_TRY(check_params(p, params));
+  p->async_t0 = std::chrono::high_resolution_clock::now();
+  DPGO_TRY(run_op(p, dpgo::OP_OPTIMIZE, *params));
+  p->async_pending = true;
+  return DPGO_OK;
+}
+
+int dpgo_optimize_result(dpgo_problem_t *p, dpgo_opt_result_t *result) {
+  DPGO_CHECK_HANDLE(p);
+  DPGO_TRY(fetch_result(p));
+  if (p->async_pending) {
+    const auto t1 = std::chrono::high_resolution_clock::now();
+    p->h_result->elapsed_ms = std::chrono::duration<double, std::milli>(t1 - p->async_t0).count();
+    p->async_pending = false;
+  }
+  if (result) *result = *p->h_result;
+  return DPGO_OK;
+}
+
+int dpgo_spmv_device(dpgo_problem_t *p, const double *X_dev, double *out_dev, int add_G) {
+  DPGO_CHECK_HANDLE(p);
+  DPGO_REQUIRE(X_dev && out_dev, DPGO_ERR_INVALID_ARG, "null argument");
+  DPGO_REQUIRE(p->have_Q, DPGO_ERR_STATE, "set_Q has not been called");
+  DPGO_CUDA(dpgo::launch_spmv(p->r, p->dh, p->n, p->d_rowptr, p->d_bcol, p->d_bval, X_dev, add_G ? p->d_G : nullptr,
+                              out_dev, p->stream));
+  return DPGO_OK;
+}
+
+int64_t dpgo_spmv_algorithmic_bytes(const dpgo_problem_t *p, int add_G) {
+  if (!p) return 0;
+  // nb*((d+1)^2*8 + 4) + (n+1)*4 + 2*r*(d+1)*n*8 (+ r*(d+1)*n*8 if G is read)
+  const int64_t dh = p->dh;
+  int64_t b = p->nb * (dh * dh * 8 + 4) + ((int64_t)p->n + 1) * 4 + 2 * (int64_t)p->r * dh * p->n * 8;
+  if (add_G) b += (int64_t)p->r * dh * p->n * 8;
+  return b;
+}
+
+// ---- boundary-pose exchange --------------------------------------------------------------------
+int dpgo_agent_set_public_poses(dpgo_problem_t *p, int num_public, const int32_t *public_pose) {
+  DPGO_CHECK_HANDLE(p);
+  DPGO_REQUIRE(num_public >= 0 && (num_public == 0 || public_pose), DPGO_ERR_INVALID_ARG, "bad public pose list");
+  for (int s = 0; s < num_public; ++s)
+    if (public_pose[s] < 0 || public_pose[s] >= p->n) return fail(DPGO_ERR_INVALID_ARG, "public pose index out of range");
+  free_dev(p->d_public);
+  p->num_public = num_public;
+  if (num_public) {
+    DPGO_CUDA(cudaMalloc(&p->d_public, sizeof(int) * num_public));
+    DPGO_CUDA(cudaMemcpy(p->d_public, public_pose, sizeof(int) * num_public, cudaMemcpyHostToDevice));
+  }
+  return DPGO_OK;
+}
+
+int dpgo_agent_pack_public(dpgo_problem_t *p, double *send_dev) {
+  DPGO_CHECK_HANDLE(p);
+  DPGO_REQUIRE(send_dev || p->num_public == 0, DPGO_ERR_INVALID_ARG, "null send buffer");
+  DPGO_CUDA(dpgo::launch_pack_tiles(p->ts, p->num_public, p->d_public, p->d_vec[dpgo::V_X0], send_dev, p->stream));
+  return DPGO_OK;
+}
+
+int dpgo_agent_set_shared_edges(dpgo_problem_t *p, int num_edges, const int32_t *local_pose, const int32_t *nbr_slot,
+                                const int32_t *outgoing, const double *T, const double *omega) {
+  DPGO_CHECK_HANDLE(p);
+  DPGO_REQUIRE(num_edges >= 0 && (num_edges == 0 || (local_pose && nbr_slot && outgoing && T && omega)),
+               DPGO_ERR_INVALID_ARG, "bad shared edge arrays");
+  const int dh = p->dh;
+  for (int e = 0; e < num_edges; ++e)
+    if (local_pose[e] < 0 || local_pose[e] >= p->n || nbr_slot[e] < 0)
+      return fail(DPGO_ERR_INVALID_ARG, "shared edge index out of range");
+  // group edges by local pose, keeping input order inside a pose (= reference accumulation order)
+  std::vector<int> order(num_edges);
+  std::iota(order.begin(), order.end(), 0);
+  std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return local_pose[x] < local_pose[y]; });
+  std::vector<int> pose_ids, pose_ptr, slot(num_edges), outg(num_edges);
+  std::vector<double> Ts((size_t)num_edges * dh * dh), oms((size_t)num_edges * dh);
+  for (int q = 0; q < num_edges; ++q) {
+    const int e = order[q];
+    if (pose_ids.empty() || pose_ids.back() != local_pose[e]) {
+      pose_ids.push_back(local_pose[e]);
+      pose_ptr.push_back(q);
+    }
+    slot[q] = nbr_slot[e];
+    outg[q] = outgoing[e] ? 1 : 0;
+    std::memcpy(&Ts[(size_t)q * dh * dh], T + (size_t)e * dh * dh, sizeof(double) * dh * dh);
+    std::memcpy(&oms[(size_t)q * dh], omega + (size_t)e * dh, sizeof(double) * dh);
+  }
+  pose_ptr.push_back(num_edges);
+  free_dev(p->d_pose_ids); free_dev(p->d_pose_ptr); free_dev(p->d_edge_slot); free_dev(p->d_edge_out);
+  free_dev(p->d_edge_T); free_dev(p->d_edge_om);
+  p->num_edges = num_edges;
+  p->num_shared_poses = (int)pose_ids.size();
+  if (num_edges) {
+    DPGO_CUDA(cudaMalloc(&p->d_pose_ids, sizeof(int) * pose_ids.size()));
+    DPGO_CUDA(cudaMalloc(&p->d_pose_ptr, sizeof(int) * pose_ptr.size()));
+    DPGO_CUDA(cudaMalloc(&p->d_edge_slot, sizeof(int) * num_edges));
+    DPGO_CUDA(cudaMalloc(&p->d_edge_out, sizeof(int) * num_edges));
+    DPGO_CUDA(cudaMalloc(&p->d_edge_T, sizeof(double) * Ts.size()));
+    DPGO_CUDA(cudaMalloc(&p->d_edge_om, sizeof(double) * oms.size()));
+    DPGO_CUDA(cudaMemcpy(p->d_pose_ids, pose_ids.data(), sizeof(int) * pose_ids.size(), cudaMemcpyHostToDevice));
+    DPGO_CUDA(cudaMemcpy(p->d_pose_ptr, pose_ptr.data(), sizeof(int) * pose_ptr.size(), cudaMemcpyHostToDevice));
+    DPGO_CUDA(cudaMemcpy(p->d_edge_slot, slot.data(), sizeof(int) * num_edges, cudaMemcpyHostToDevice));
+    DPGO_CUDA(cudaMemcpy(p->d_edge_out, outg.data(), sizeof(int) * num_edges, cudaMemcpyHostToDevice));
+    DPGO_CUDA(cudaMemcpy(p->d_edge_T, Ts.data(), sizeof(double) * Ts.size(), cudaMemcpyHostToDevice));
+    DPGO_CUDA(cudaMemcpy(p->d_edge_om, oms.data(), sizeof(double) * oms.size(), cudaMemcpyHostToDevice));
+  }
+  return DPGO_OK;
+}
+
+int dpgo_agent_build_G(dpgo_problem_t *p, const double *gathered_dev, int64_t num_slots) {
+  DPGO_CHECK_HANDLE(p);
+  DPGO_REQUIRE(gathered_dev || p->num_edges == 0, DPGO_ERR_INVALID_ARG, "null gathered buffer");
+  (void)num_slots;
+  DPGO_CUDA(cudaMemsetAsync(p->d_G, 0, p->vec_bytes(), p->stream));
+  if (p->num_edges)
+    DPGO_CUDA(dpgo::launch_build_G(p->r, p->dh, p->num_shared_poses, p->d_pose_ids, p->d_pose_ptr, p->d_edge_slot,
+                                   p->d_edge_out, p->d_edge_T, p->d_edge_om, gathered_dev, p->d_G, p->stream));
+  return DPGO_OK;
+}
+
+int dpgo_agent_f_rgradnorm_resident(dpgo_problem_t *p, double *f_out, double *norm_out) {
+  DPGO_CHECK_HANDLE(p);
+  dpgo_opt_params_t prm;
+  dpgo_opt_params_default(&prm);
+  prm.precond = DPGO_PRECOND_NONE;
+  DPGO_TRY(run_op(p, dpgo::OP_EVAL, prm));
+  DPGO_TRY(fetch_result(p));
+  if (f_out) *f_out = p->h_result->f_init;
+  if (norm_out) *norm_out = p->h_result->gradnorm_init;
+  return DPGO_OK;
+}
+
+}  // extern "C"

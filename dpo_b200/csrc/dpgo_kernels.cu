@@ -1,0 +1,895 @@
+// dpgo_kernels.cu -- sm_100a kernels of the pose-graph hot path.
+//
+//  k_optimize<R,DH> : ONE persistent cooperative kernel per QuadraticOptimizer::optimize() call
+//                     (ref: src/QuadraticOptimizer.cpp:34-149 + ROPTLIB RTRNewton/tCG).  All phases
+//                     -- fused [X.Q + G, f, tangent projection, |g|, preconditioner] passes,
+//                     Riemannian Hessian-vector products of the truncated-CG loop, vector updates,
+//                     QF retraction -- run inside it, separated by grid barriers; scalar
+//                     reductions are fixed-order (deterministic) and every CTA replays the same
+//                     scalar control flow.  The host sees only the result record.
+//  k_spmv<R,DH>     : the Q.X product alone (Out = X Q [+ G]) -- the roofline kernel.
+//  small kernels    : Stiefel (polar) projection, public-pose packing, G assembly.
+#include "dpgo_device.cuh"
+#include "dpgo_kernels.cuh"
+#include <cooperative_groups.h>
+
+namespace dpgo {
+
+// ---------------------------------------------------------------------------------------------
+// phase-end reduction: block partials -> global partials -> grid barrier -> every CTA sums all
+// partials in the same fixed order, so all CTAs hold bit-identical scalars.
+// ---------------------------------------------------------------------------------------------
+struct BlockCtx {
+  double *sm_warp;    // [nwarps * NRED]
+  double *sm_out;     // [NRED]
+  unsigned epoch;
+  int parity;
+};
+
+__device__ __forceinline__ void phase_end(const KParams &kp, BlockCtx &bc, double (&acc)[NRED]) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+#pragma unroll
+  for (int q = 0; q < NRED; ++q) {
+    double v = warp_sum(acc[q]);
+    if (lane == 0) bc.sm_warp[warp * NRED + q] = v;
+  }
+  __syncthreads();
+  double *slot = kp.partials + (size_t)bc.parity * kp.grid * NRED;
+  if (threadIdx.x < NRED) {
+    double s = 0.0;
+    for (int w = 0; w < nwarps; ++w) s += bc.sm_warp[w * NRED + threadIdx.x];
+    slot[(size_t)blockIdx.x * NRED + threadIdx.x] = s;
+  }
+  grid_barrier(kp.bar_counter, bc.epoch);
+  if (warp == 0) {
+#pragma unroll
+    for (int q = 0; q < NRED; ++q) {
+      double s = 0.0;
+      for (int c = lane; c < kp.grid; c += 32) s += __ldcg(slot + (size_t)c * NRED + q);
+      s = warp_sum(s);
+      if (lane == 0) bc.sm_out[q] = s;
+    }
+  }
+  __syncthreads();
+#pragma unroll
+  for (int q = 0; q < NRED; ++q) acc[q] = bc.sm_out[q];
+  __syncthreads();           // sm_out / sm_warp may be rewritten by the next phase
+  bc.parity ^= 1;
+}
+
+// row iteration helper: warp-uniform loop, sub-groups past the end run with active == false
+template <int R> struct RowIter {
+  static constexpr int SG = SubGroup<R>::SG;
+  int r0, r1, stride, jb, sgw, a, c;
+  __device__ RowIter(const KParams &kp) {
+    r0 = ld_const(kp.cta_rows + blockIdx.x);
+    r1 = ld_const(kp.cta_rows + blockIdx.x + 1);
+    const int lane = threadIdx.x & 31;
+    constexpr int SGW = 32 / SG;                 // sub-groups per warp
+    sgw = lane / SG;
+    stride = (blockDim.x >> 5) * SGW;
+    jb = r0 + (threadIdx.x >> 5) * SGW;
+    const int l = lane & (SG - 1);
+    a = l >> 2;
+    c = l & 3;
+  }
+};
+
+// ---------------------------------------------------------------------------------------------
+// Phase E: everything that is needed at a base point in ONE pass over Q
+//   EG = X Q + G, f = 0.5 <XQ, X> + <X, G>, S = sym(Y^T EG_Y), RG = P_X(EG), |RG|^2,
+//   Z0 = P_X(M^-1 RG) for the pose-local preconditioners, <Z0, RG>.
+// (ref: QuadraticProblem::f / EucGrad / RieGrad, src/QuadraticProblem.cpp:50-66,89-101; the reference
+//  spends 5 separate X.Q products on these values per optimize() call.)
+// acc: [0] <XQ,X>  [1] <X,G>  [2] |RG|^2  [3] <Z0,RG>
+// ---------------------------------------------------------------------------------------------
+template <int R, int DH>
+__device__ void phase_eval(const KParams &kp, int cb, bool save_xin, int precond, double (&acc)[NRED]) {
+  constexpr int TS = R * DH;
+  const double *X = kp.v[V_X0 + cb];
+  double *EG = kp.v[V_EG0 + cb], *RG = kp.v[V_RG0 + cb], *Z0 = kp.v[V_Z00 + cb], *S = kp.S[cb];
+  RowIter<R> it(kp);
+  const bool valid = (it.a < R) && (it.c < DH);
+  const int e = it.c * R + it.a;
+  for (int jb = it.jb; jb < it.r1; jb += it.stride) {
+    const int j = jb + it.sgw;
+    const bool act = (j < it.r1);
+    const int js = act ? j : it.r1 - 1;
+    const bool ld = act && valid;
+    double xq = gather_tile<R, DH, true, false>(kp.rowptr, kp.bcol, kp.bval, X, nullptr, 0.0, js, it.a, it.c);
+    const size_t idx = (size_t)js * TS + e;
+    const double x = ld ? __ldcg(X + idx) : 0.0;
+    const double g = ld ? __ldcg(kp.G + idx) : 0.0;
+    if (!ld) xq = 0.0;
+    const double eg = xq + g;
+    acc[0] = fma(xq, x, acc[0]);
+    acc[1] = fma(x, g, acc[1]);
+    double ya[3], sym[3];
+    const double rg = tangent_project_elem<R, DH>(x, eg, it.a, it.c, ya, sym);
+    if (ld) {
+      EG[idx] = eg;
+      RG[idx] = rg;
+      if (save_xin) kp.v[V_XIN][idx] = x;
+      acc[2] = fma(rg, rg, acc[2]);
+    }
+    if (act && it.a == 0 && it.c < 3) {
+      double *s = S + (size_t)js * 9 + it.c * 3;
+      s[0] = sym[0]; s[1] = sym[1]; s[2] = sym[2];
+    }
+    if (precond != DPGO_PRECOND_DENSE_EXACT) {
+      double z0 = rg;
+      if (precond == DPGO_PRECOND_BLOCK_JACOBI) {
+        double t = jacobi_elem<R, DH>(kp.dinv, js, ld ? rg : 0.0, it.a, it.c);
+        double ya2[3], sym2[3];
+        z0 = tangent_project_elem<R, DH>(x, t, it.a, it.c, ya2, sym2);
+      }
+      if (ld) {
+        Z0[idx] = z0;
+        acc[3] = fma(z0, rg, acc[3]);
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Phase H: Riemannian Hessian-vector product of the tCG direction (ref: QuadraticProblem::
+// EucHessianEta, src/QuadraticProblem.cpp:68-73, + ROPTLIB Stiefel::EucHvToHv + projection):
+//   delta_new = -zsrc + beta * delta_old      (formed on the fly for neighbour tiles, stored for own)
+//   HD = P_X( delta_new Q - [delta_new_Y S]_pose ),   acc[0] = <delta_new, HD>
+// If onfly == false the operand is read as is from `zsrc` (single-operation entry point).
+// ---------------------------------------------------------------------------------------------
+template <int R, int DH>
+__device__ void phase_hess(const KParams &kp, int cb, const double *zsrc, const double *dold, double *dnew,
+                           double beta, bool onfly, double (&acc)[NRED]) {
+  constexpr int TS = R * DH;
+  constexpr int D = DH - 1;
+  const double *X = kp.v[V_X0 + cb];
+  const double *S = kp.S[cb];
+  double *HD = kp.v[V_HD];
+  RowIter<R> it(kp);
+  const bool valid = (it.a < R) && (it.c < DH);
+  const int e = it.c * R + it.a;
+  for (int jb = it.jb; jb < it.r1; jb += it.stride) {
+    const int j = jb + it.sgw;
+    const bool act = (j < it.r1);
+    const int js = act ? j : it.r1 - 1;
+    const bool ld = act && valid;
+    double hq;
+    if (onfly) hq = gather_tile<R, DH, true, true>(kp.rowptr, kp.bcol, kp.bval, zsrc, dold, beta, js, it.a, it.c);
+    else hq = gather_tile<R, DH, true, false>(kp.rowptr, kp.bcol, kp.bval, zsrc, nullptr, 0.0, js, it.a, it.c);
+    const size_t idx = (size_t)js * TS + e;
+    double dl = 0.0;
+    if (ld) {
+      dl = __ldcg(zsrc + idx);
+      if (onfly) {
+        dl = -dl;
+        if (beta != 0.0) dl = fma(beta, __ldcg(dold + idx), dl);
+        dnew[idx] = dl;
+      }
+    }
+    const double x = ld ? __ldcg(X + idx) : 0.0;
+    const bool rot = ld && (it.c < D);
+    double s0 = 0, s1 = 0, s2 = 0;
+    if (rot) {
+      const double *s = S + (size_t)js * 9 + it.c * 3;
+      s0 = __ldcg(s); s1 = __ldcg(s + 1); s2 = __ldcg(s + 2);
+    }
+    const double dr = rot ? dl : 0.0;
+    const double d0 = quad_get(dr, 0), d1 = quad_get(dr, 1), d2 = (D > 2) ? quad_get(dr, 2) : 0.0;
+    double w = ld ? hq : 0.0;
+    if (rot) w -= (d0 * s0 + d1 * s1 + d2 * s2);
+    double ya[3], sym[3];
+    const double hd = tangent_project_elem<R, DH>(x, w, it.a, it.c, ya, sym);
+    if (ld) {
+      HD[idx] = hd;
+      acc[0] = fma(dl, hd, acc[0]);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Phase U: eta += alpha delta, res += alpha HD, |res|^2 and (pose-local preconditioners)
+// z = P_X(M^-1 res), <z,res>.   acc: [0] |res|^2  [1] <z,res>
+// ---------------------------------------------------------------------------------------------
+template <int R, int DH>
+__device__ void phase_update(const KParams &kp, int cb, const double *dcur, double alpha, bool first, int precond,
+                             double (&acc)[NRED]) {
+  constexpr int TS = R * DH;
+  const double *X = kp.v[V_X0 + cb];
+  const double *RG = kp.v[V_RG0 + cb];
+  double *ETA = kp.v[V_ETA], *RES = kp.v[V_RES], *Z = kp.v[V_Z];
+  const double *HD = kp.v[V_HD];
+  RowIter<R> it(kp);
+  const bool valid = (it.a < R) && (it.c < DH);
+  const int e = it.c * R + it.a;
+  for (int jb = it.jb; jb < it.r1; jb += it.stride) {
+    const int j = jb + it.sgw;
+    const bool act = (j < it.r1);
+    const int js = act ? j : it.r1 - 1;
+    const bool ld = act && valid;
+    const size_t idx = (size_t)js * TS + e;
+    double res = 0.0, x = 0.0;
+    if (ld) {
+      const double dl = __ldcg(dcur + idx), hd = __ldcg(HD + idx);
+      const double eta0 = first ? 0.0 : __ldcg(ETA + idx);
+      const double res0 = first ? __ldcg(RG + idx) : __ldcg(RES + idx);
+      res = fma(alpha, hd, res0);
+      ETA[idx] = fma(alpha, dl, eta0);
+      RES[idx] = res;
+      acc[0] = fma(res, res, acc[0]);
+      x = __ldcg(X + idx);
+    }
+    if (precond != DPGO_PRECOND_DENSE_EXACT) {
+      double z = res;
+      if (precond == DPGO_PRECOND_BLOCK_JACOBI) {
+        double t = jacobi_elem<R, DH>(kp.dinv, js, res, it.a, it.c);
+        double ya[3], sym[3];
+        z = tangent_project_elem<R, DH>(x, t, it.a, it.c, ya, sym);
+      }
+      if (ld) {
+        Z[idx] = z;
+        acc[1] = fma(z, res, acc[1]);
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Dense-inverse preconditioner (parity mode; ref: QuadraticProblem::PreConditioner,
+// src/QuadraticProblem.cpp:75-87 = CHOLMOD solve with Q+0.1I, then projection):
+//   phase_dense : T = V * Pinv      (Pinv symmetric N x N, streamed once, coalesced columns)
+//   phase_pz    : Z = P_X(T), acc[0] = <Z, V>
+// ---------------------------------------------------------------------------------------------
+template <int R, int CT>
+__device__ void dense_cols(const KParams &kp, const double *V, double *T, double *sV, int KC, int c0, int c1) {
+  const int N = kp.N;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  const int ngroups = (c1 - c0 + CT - 1) / CT;
+  const int rounds = (ngroups + nwarps - 1) / nwarps;
+  for (int rd = 0; rd < rounds; ++rd) {
+    const int grp = rd * nwarps + warp;
+    const int col = c0 + grp * CT;
+    const bool wact = grp < ngroups;
+    double acc[CT][R];
+#pragma unroll
+    for (int t = 0; t < CT; ++t)
+#pragma unroll
+      for (int a = 0; a < R; ++a) acc[t][a] = 0.0;
+    for (int k0 = 0; k0 < N; k0 += KC) {
+      const int kn = min(KC, N - k0);
+      __syncthreads();
+      for (int q = threadIdx.x; q < kn * R; q += blockDim.x) sV[q] = __ldcg(V + (size_t)k0 * R + q);
+      __syncthreads();
+      if (wact) {
+        for (int kk = lane; kk < kn; kk += 32) {
+          double p[CT];
+#pragma unroll
+          for (int t = 0; t < CT; ++t)
+            p[t] = (col + t < c1) ? ld_const(kp.pinv + (size_t)(col + t) * N + k0 + kk) : 0.0;
+#pragma unroll
+          for (int a = 0; a < R; ++a) {
+            const double v = sV[kk * R + a];
+#pragma unroll
+            for (int t = 0; t < CT; ++t) acc[t][a] = fma(v, p[t], acc[t][a]);
+          }
+        }
+      }
+    }
+    if (wact) {
+#pragma unroll
+      for (int t = 0; t < CT; ++t)
+#pragma unroll
+        for (int a = 0; a < R; ++a) {
+          const double s = warp_sum(acc[t][a]);
+          if (lane == 0 && col + t < c1) T[(size_t)(col + t) * R + a] = s;
+        }
+    }
+  }
+}
+
+template <int R> __device__ void phase_dense(const KParams &kp, const double *V, double *T, double *sV, int KC) {
+  const int N = kp.N;
+  const int per = (N + kp.grid - 1) / kp.grid;
+  const int c0 = min(N, (int)blockIdx.x * per), c1 = min(N, c0 + per);
+  const int nwarps = blockDim.x >> 5;
+  if (c1 - c0 >= 4 * nwarps) dense_cols<R, 4>(kp, V, T, sV, KC, c0, c1);
+  else dense_cols<R, 1>(kp, V, T, sV, KC, c0, c1);
+}
+
+template <int R, int DH>
+__device__ void phase_pz(const KParams &kp, int cb, const double *V, const double *T, double *Zout,
+                         double (&acc)[NRED]) {
+  constexpr int TS = R * DH;
+  const double *X = kp.v[V_X0 + cb];
+  RowIter<R> it(kp);
+  const bool valid = (it.a < R) && (it.c < DH);
+  const int e = it.c * R + it.a;
+  for (int jb = it.jb; jb < it.r1; jb += it.stride) {
+    const int j = jb + it.sgw;
+    const bool act = (j < it.r1);
+    const int js = act ? j : it.r1 - 1;
+    const bool ld = act && valid;
+    const size_t idx = (size_t)js * TS + e;
+    const double x = ld ? __ldcg(X + idx) : 0.0;
+    const double t = ld ? __ldcg(T + idx) : 0.0;
+    double ya[3], sym[3];
+    const double z = tangent_project_elem<R, DH>(x, t, it.a, it.c, ya, sym);
+    if (ld) {
+      Zout[idx] = z;
+      acc[0] = fma(z, __ldcg(V + idx), acc[0]);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Phase RT: candidate X' = R_X(eta_final) with eta_final = eta + tau * delta (tau = 0 unless tCG
+// stopped on the trust-region boundary / negative curvature), and the model-decrease dots
+//   acc[0] = <eta, g>, acc[1] = <eta, H eta> with H eta = (res - g) + tau * HD (tCG recurrences).
+// mode 1 (RGD, ref src/QuadraticOptimizer.cpp:124-149): eta = -step * RG.
+// mode 2: eta read as is from V_AUX (single-operation entry point).
+// ---------------------------------------------------------------------------------------------
+template <int R, int DH>
+__device__ void phase_retract(const KParams &kp, int cb, int mode, const double *dcur, double tau, bool eta_zero,
+                              double step, double (&acc)[NRED]) {
+  constexpr int TS = R * DH;
+  const double *X = kp.v[V_X0 + cb];
+  const double *RG = kp.v[V_RG0 + cb];
+  double *X2 = kp.v[V_X0 + (1 - cb)];
+  RowIter<R> it(kp);
+  const bool valid = (it.a < R) && (it.c < DH);
+  const int e = it.c * R + it.a;
+  for (int jb = it.jb; jb < it.r1; jb += it.stride) {
+    const int j = jb + it.sgw;
+    const bool act = (j < it.r1);
+    const int js = act ? j : it.r1 - 1;
+    const bool ld = act && valid;
+    const size_t idx = (size_t)js * TS + e;
+    double w = 0.0;
+    if (ld) {
+      const double x = __ldcg(X + idx);
+      double eta;
+      if (mode == 1) {
+        eta = -step * __ldcg(RG + idx);
+      } else if (mode == 2) {
+        eta = __ldcg(kp.v[V_AUX] + idx);
+      } else {
+        const double g = __ldcg(RG + idx);
+        eta = eta_zero ? 0.0 : __ldcg(kp.v[V_ETA] + idx);
+        double heta = eta_zero ? 0.0 : (__ldcg(kp.v[V_RES] + idx) - g);
+        if (tau != 0.0) {
+          eta = fma(tau, __ldcg(dcur + idx), eta);
+          heta = fma(tau, __ldcg(kp.v[V_HD] + idx), heta);
+        }
+        acc[0] = fma(eta, g, acc[0]);
+        acc[1] = fma(eta, heta, acc[1]);
+      }
+      w = x + eta;
+    }
+    const double q = qf_retract_elem<R, DH>(w, it.a, it.c);
+    if (ld) X2[idx] = q;
+  }
+}
+
+// Final phase: make X0 hold the result and accumulate |X_out - X_in|^2 (ref: relativeChange,
+// src/QuadraticOptimizer.cpp:54).
+template <int R, int DH> __device__ void phase_final(const KParams &kp, int cur, double (&acc)[NRED]) {
+  constexpr int TS = R * DH;
+  RowIter<R> it(kp);
+  const bool valid = (it.a < R) && (it.c < DH);
+  const int e = it.c * R + it.a;
+  for (int jb = it.jb; jb < it.r1; jb += it.stride) {
+    const int j = jb + it.sgw;
+    if (j < it.r1 && valid) {
+      const size_t idx = (size_t)j * TS + e;
+      const double x = __ldcg(kp.v[V_X0 + cur] + idx);
+      const double d = x - __ldcg(kp.v[V_XIN] + idx);
+      acc[0] = fma(d, d, acc[0]);
+      if (cur != 0) kp.v[V_X0][idx] = x;
+    }
+  }
+}
+
+__device__ __forceinline__ void zero(double (&acc)[NRED]) {
+#pragma unroll
+  for (int q = 0; q < NRED; ++q) acc[q] = 0.0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// The persistent kernel
+// ---------------------------------------------------------------------------------------------
+template <int R, int DH> __global__ void __launch_bounds__(OPT_THREADS, 1) k_optimize(const KParams kp) {
+  extern __shared__ double smem[];
+  BlockCtx bc;
+  bc.sm_warp = smem;
+  bc.sm_out = smem + (OPT_THREADS / 32) * NRED;
+  double *sV = bc.sm_out + NRED;                // dense-preconditioner staging (KC * R doubles)
+  const int KC = 1024;
+  bc.epoch = *kp.bar_epoch;
+  bc.parity = 0;
+  const dpgo_opt_params_t prm = kp.prm;
+  const int precond = prm.precond;
+  double acc[NRED];
+  dpgo_opt_result_t res;
+  res.success = 0; res.tcg_status = DPGO_TCG_NOT_RUN; res.tcg_iterations = 0; res.outer_iterations = 0;
+  res.rejections = 0; res.spmv_passes = 0;
+  res.f_init = res.gradnorm_init = res.f_opt = res.gradnorm_opt = res.relative_change = res.elapsed_ms = 0.0;
+
+  int cur = 0;   // which X buffer holds the current iterate
+
+  // ---- single-operation entry points -------------------------------------------------------
+  if (kp.op == OP_PRECON) {
+    if (precond == DPGO_PRECOND_DENSE_EXACT) {
+      phase_dense<R>(kp, kp.v[V_AUX], kp.v[V_T], sV, KC);
+      zero(acc); phase_end(kp, bc, acc);
+      zero(acc); phase_pz<R, DH>(kp, 0, kp.v[V_AUX], kp.v[V_T], kp.v[V_Z], acc);
+      phase_end(kp, bc, acc);
+    } else {
+      // reuse phase_update with res := AUX (first = false, alpha = 0 would need RES); do it directly
+      constexpr int TS = R * DH;
+      RowIter<R> it(kp);
+      const bool valid = (it.a < R) && (it.c < DH);
+      const int e = it.c * R + it.a;
+      for (int jb = it.jb; jb < it.r1; jb += it.stride) {
+        const int j = jb + it.sgw;
+        const bool act = (j < it.r1);
+        const int js = act ? j : it.r1 - 1;
+        const bool ld = act && valid;
+        const size_t idx = (size_t)js * TS + e;
+        const double x = ld ? __ldcg(kp.v[V_X0] + idx) : 0.0;
+        double t = ld ? __ldcg(kp.v[V_AUX] + idx) : 0.0;
+        if (precond == DPGO_PRECOND_BLOCK_JACOBI) t = jacobi_elem<R, DH>(kp.dinv, js, t, it.a, it.c);
+        double ya[3], sym[3];
+        const double z = tangent_project_elem<R, DH>(x, t, it.a, it.c, ya, sym);
+        if (ld) kp.v[V_Z][idx] = z;
+      }
+      zero(acc); phase_end(kp, bc, acc);
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) *kp.bar_epoch = bc.epoch;
+    return;
+  }
+  if (kp.op == OP_RETRACT) {
+    zero(acc);
+    phase_retract<R, DH>(kp, 0, 2, nullptr, 0.0, false, 0.0, acc);
+    phase_end(kp, bc, acc);
+    if (blockIdx.x == 0 && threadIdx.x == 0) *kp.bar_epoch = bc.epoch;
+    return;
+  }
+
+  // ---- statistics at the input point (ref: src/QuadraticOptimizer.cpp:36-37) -------------------
+  zero(acc);
+  phase_eval<R, DH>(kp, 0, true, precond, acc);
+  phase_end(kp, bc, acc);
+  res.spmv_passes++;
+  double f1 = 0.5 * acc[0] + acc[1];
+  double gn = sqrt(acc[2]);
+  double zr0 = acc[3];
+  res.f_init = f1;
+  res.gradnorm_init = gn;
+  res.f_opt = f1;
+  res.gradnorm_opt = gn;
+
+  if (kp.op == OP_EVAL) {
+    res.success = 1;
+    if (blockIdx.x == 0 && threadIdx.x == 0) { *kp.result = res; *kp.bar_epoch = bc.epoch; }
+    return;
+  }
+  if (kp.op == OP_RHESS) {
+    zero(acc);
+    phase_hess<R, DH>(kp, 0, kp.v[V_AUX], nullptr, nullptr, 0.0, false, acc);
+    phase_end(kp, bc, acc);
+    if (blockIdx.x == 0 && threadIdx.x == 0) { *kp.result = res; *kp.bar_epoch = bc.epoch; }
+    return;
+  }
+
+  if (prm.algorithm == DPGO_ALG_RGD) {
+    // ---- one fixed-step Riemannian gradient-descent step (ref :124-149) ----------------------
+    zero(acc);
+    phase_retract<R, DH>(kp, 0, 1, nullptr, 0.0, false, prm.rgd_stepsize, acc);
+    phase_end(kp, bc, acc);
+    zero(acc);
+    phase_eval<R, DH>(kp, 1, false, DPGO_PRECOND_NONE, acc);
+    phase_end(kp, bc, acc);
+    res.spmv_passes++;
+    res.f_opt = 0.5 * acc[0] + acc[1];
+    res.gradnorm_opt = sqrt(acc[2]);
+    res.outer_iterations = 1;
+    cur = 1;
+  } else if (gn >= prm.tr_tolerance) {           // ref :67-70 early exit otherwise
+    // ---- Riemannian trust region ------------------------------------------------------------
+    const bool single = (prm.tr_iterations == 1);      // ref :92-110 shrink-until-accepted mode
+    double Delta = prm.tr_initial_radius;
+    const double Delta_max = single ? Delta : 5.0 * prm.tr_initial_radius;   // ref :80-81,:96-97
+    int total_steps = 0;
+    int cb = 0;                      // base buffer
+    bool z0_valid = (precond != DPGO_PRECOND_DENSE_EXACT);
+    int iter = 0;
+    while (true) {
+      // -- z0 = M^-1 g for the dense preconditioner (pose-local ones were fused into phase E)
+      if (!z0_valid) {
+        phase_dense<R>(kp, kp.v[V_RG0 + cb], kp.v[V_T], sV, KC);
+        zero(acc); phase_end(kp, bc, acc);
+        zero(acc); phase_pz<R, DH>(kp, cb, kp.v[V_RG0 + cb], kp.v[V_T], kp.v[V_Z00 + cb], acc);
+        phase_end(kp, bc, acc);
+        zr0 = acc[0];
+        z0_valid = true;
+      }
+      // -- truncated CG (ROPTLIB SolversTR::tCG_TR; theta = 1, kappa = 0.1, Min_Inner_Iter = 0)
+      double z_r = zr0, d_Pd = zr0, e_Pd = 0.0, e_Pe = 0.0;
+      const double n0 = gn;
+      double beta = 0.0, tau = 0.0;
+      const double *zsrc = kp.v[V_Z00 + cb];
+      int pd = 0;                                  // delta_old lives in V_D0 + pd
+      bool eta_zero = true;
+      int status = DPGO_TCG_MAXITER;
+      const double *dcur = nullptr;
+      for (int j = 0; j < prm.tr_max_inner; ++j) {
+        double *dnew = kp.v[V_D0 + (1 - pd)];
+        zero(acc);
+        phase_hess<R, DH>(kp, cb, zsrc, kp.v[V_D0 + pd], dnew, beta, true, acc);
+        phase_end(kp, bc, acc);
+        res.spmv_passes++;
+        res.tcg_iterations++;
+        pd = 1 - pd;
+        dcur = dnew;
+        const double d_Hd = acc[0];
+        const double alpha = z_r / d_Hd;
+        const double e_new = e_Pe + 2.0 * alpha * e_Pd + alpha * alpha * d_Pd;
+        if (d_Hd <= 0.0 || e_new >= Delta * Delta) {
+          tau = (-e_Pd + sqrt(e_Pd * e_Pd + d_Pd * (Delta * Delta - e_Pe))) / d_Pd;
+          status = (d_Hd <= 0.0) ? DPGO_TCG_NEGCURVTURE : DPGO_TCG_EXCREGION;
+          break;
+        }
+        e_Pe = e_new;
+        zero(acc);
+        phase_update<R, DH>(kp, cb, dcur, alpha, eta_zero, precond, acc);
+        phase_end(kp, bc, acc);
+        eta_zero = false;
+        const double nr = sqrt(acc[0]);
+        const double n0t = n0;                         // n0^theta, theta = 1
+        if (nr <= n0 * fmin(n0t, 0.1)) {
+          status = (0.1 < n0t) ? DPGO_TCG_LCON : DPGO_TCG_SCON;
+          break;
+        }
+        double zr_new = acc[1];
+        if (precond == DPGO_PRECOND_DENSE_EXACT) {
+          phase_dense<R>(kp, kp.v[V_RES], kp.v[V_T], sV, KC);
+          zero(acc); phase_end(kp, bc, acc);
+          zero(acc); phase_pz<R, DH>(kp, cb, kp.v[V_RES], kp.v[V_T], kp.v[V_Z], acc);
+          phase_end(kp, bc, acc);
+          zr_new = acc[0];
+        }
+        beta = zr_new / z_r;
+        z_r = zr_new;
+        zsrc = kp.v[V_Z];
+        e_Pd = beta * (e_Pd + alpha * d_Pd);
+        d_Pd = z_r + beta * beta * d_Pd;
+      }
+      res.tcg_status = status;
+      res.outer_iterations++;
+      // -- candidate point, model decrease, actual decrease
+      zero(acc);
+      phase_retract<R, DH>(kp, cb, 0, dcur, tau, eta_zero, 0.0, acc);
+      phase_end(kp, bc, acc);
+      const double denom = -acc[0] - 0.5 * acc[1];
+      zero(acc);
+      phase_eval<R, DH>(kp, 1 - cb, false, precond, acc);
+      phase_end(kp, bc, acc);
+      res.spmv_passes++;
+      const double f2 = 0.5 * acc[0] + acc[1];
+      const double gn2 = sqrt(acc[2]);
+      const double rho = (denom != 0.0) ? (f1 - f2) / denom : -1.0;
+      const bool accepted = rho > 0.1;                 // ROPTLIB Acceptence_Rho
+      if (single) {
+        if (accepted) {
+          cb = 1 - cb; res.f_opt = f2; res.gradnorm_opt = gn2;
+          break;
+        }
+        res.rejections++;
+        if (total_steps > 10) break;                   // ref :101-103 return the initial guess
+        Delta *= 0.25;                                 // ref :104-107
+        total_steps++;
+      } else {
+        // ROPTLIB SolversTR radius update (Shrinked_tau = 0.25, Magnified_tau = 2)
+        if (rho < 0.25) Delta *= 0.25;
+        else if (rho > 0.75 && (status == DPGO_TCG_NEGCURVTURE || status == DPGO_TCG_EXCREGION))
+          Delta = fmin(2.0 * Delta, Delta_max);
+        if (accepted) {
+          cb = 1 - cb; f1 = f2; gn = gn2; zr0 = acc[3];
+          res.f_opt = f2; res.gradnorm_opt = gn2;
+          z0_valid = (precond != DPGO_PRECOND_DENSE_EXACT);
+        } else {
+          res.rejections++;
+        }
+        ++iter;
+        if (gn < prm.tr_tolerance || iter >= prm.tr_iterations) break;
+      }
+    }
+    cur = cb;
+  }
+
+  zero(acc);
+  phase_final<R, DH>(kp, cur, acc);
+  phase_end(kp, bc, acc);
+  res.relative_change = sqrt(acc[0] / (double)kp.n);
+  res.success = 1;
+  if (blockIdx.x == 0 && threadIdx.x == 0) { *kp.result = res; *kp.bar_epoch = bc.epoch; }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Stand-alone Q.X product: Out = X Q (+ G).  One sub-group per pose tile, plain grid.
+// ---------------------------------------------------------------------------------------------
+constexpr int SPMV_THREADS = 256;
+
+template <int R, int DH>
+__global__ void __launch_bounds__(SPMV_THREADS) k_spmv(int n, const int *__restrict__ rowptr,
+                                                       const int *__restrict__ bcol,
+                                                       const double *__restrict__ bval,
+                                                       const double *__restrict__ X,
+                                                       const double *__restrict__ G, double *__restrict__ out) {
+  constexpr int SG = SubGroup<R>::SG;
+  constexpr int TS = R * DH;
+  const int lane = threadIdx.x & 31;
+  const int l = lane & (SG - 1), a = l >> 2, c = l & 3;
+  const int sg_global = (blockIdx.x * SPMV_THREADS + threadIdx.x) / SG;
+  const int j = sg_global;
+  const bool act = j < n;
+  const int js = act ? j : n - 1;
+  double v = gather_tile<R, DH, false, false>(rowptr, bcol, bval, X, nullptr, 0.0, js, a, c);
+  if (act && a < R && c < DH) {
+    const size_t idx = (size_t)js * TS + c * R + a;
+    if (G != nullptr) v += __ldg(G + idx);
+    out[idx] = v;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Stiefel (polar-factor) projection per pose, ref: LiftedSEManifold::project,
+// src/manifold/LiftedSEManifold.cpp:34-45 + projectToStiefelManifold, src/DPGO_utils.cpp:479-485
+// (U V^T of the thin SVD = polar factor).  One thread per pose: polar factor via the
+// eigen-decomposition-free Newton-Schulz-stabilised iteration  Y <- Y (1.5 I - 0.5 Y^T Y) after an
+// initial scaling, switched to the exact form  Y (Y^T Y)^{-1/2}  through a Jacobi eigen-solve of
+// the d x d Gram matrix (cyclic Jacobi, converges quadratically; d <= 3).
+// ---------------------------------------------------------------------------------------------
+template <int R, int DH> __global__ void k_stiefel_project(int n, const double *__restrict__ M, double *__restrict__ out) {
+  constexpr int D = DH - 1;
+  constexpr int TS = R * DH;
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= n) return;
+  double y[D][R];
+#pragma unroll
+  for (int c = 0; c < D; ++c)
+#pragma unroll
+    for (int a = 0; a < R; ++a) y[c][a] = M[(size_t)j * TS + c * R + a];
+  // Gram matrix A = Y^T Y (symmetric D x D)
+  double A[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}}, V[3][3] = {{1, 0, 0}, {0, 1, 0}, {0, 0, 1}};
+#pragma unroll
+  for (int p = 0; p < D; ++p)
+#pragma unroll
+    for (int q = 0; q < D; ++q) {
+      double s = 0;
+#pragma unroll
+      for (int a = 0; a < R; ++a) s = fma(y[p][a], y[q][a], s);
+      A[p][q] = s;
+    }
+  // cyclic Jacobi eigen-decomposition A = V diag(w) V^T
+  for (int sweep = 0; sweep < 12; ++sweep) {
+    double offd = 0;
+#pragma unroll
+    for (int p = 0; p < D; ++p)
+#pragma unroll
+      for (int q = p + 1; q < D; ++q) offd += A[p][q] * A[p][q];
+    if (offd < 1e-300) break;
+#pragma unroll
+    for (int p = 0; p < D; ++p)
+#pragma unroll
+      for (int q = p + 1; q < D; ++q) {
+        const double apq = A[p][q];
+        if (apq == 0.0) continue;
+        const double theta = (A[q][q] - A[p][p]) / (2.0 * apq);
+        const double t = (theta >= 0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
+        const double cs = 1.0 / sqrt(t * t + 1.0), sn = t * cs;
+#pragma unroll
+        for (int k = 0; k < D; ++k) {      // A <- A J
+          const double akp = A[k][p], akq = A[k][q];
+          A[k][p] = cs * akp - sn * akq;
+          A[k][q] = sn * akp + cs * akq;
+        }
+#pragma unroll
+        for (int k = 0; k < D; ++k) {      // A <- J^T A
+          const double apk = A[p][k], aqk = A[q][k];
+          A[p][k] = cs * apk - sn * aqk;
+          A[q][k] = sn * apk + cs * aqk;
+        }
+#pragma unroll
+        for (int k = 0; k < D; ++k) {
+          const double vkp = V[k][p], vkq = V[k][q];
+          V[k][p] = cs * vkp - sn * vkq;
+          V[k][q] = sn * vkp + cs * vkq;
+        }
+      }
+  }
+  // B = V diag(1/sqrt(w)) V^T ; out = Y B
+  double B[3][3];
+#pragma unroll
+  for (int p = 0; p < D; ++p)
+#pragma unroll
+    for (int q = 0; q < D; ++q) {
+      double s = 0;
+#pragma unroll
+      for (int k = 0; k < D; ++k) s += V[p][k] * V[q][k] * (1.0 / sqrt(A[k][k]));
+      B[p][q] = s;
+    }
+#pragma unroll
+  for (int c = 0; c < D; ++c)
+#pragma unroll
+    for (int a = 0; a < R; ++a) {
+      double s = 0;
+#pragma unroll
+      for (int k = 0; k < D; ++k) s = fma(y[k][a], B[k][c], s);
+      out[(size_t)j * TS + c * R + a] = s;
+    }
+#pragma unroll
+  for (int a = 0; a < R; ++a) out[(size_t)j * TS + D * R + a] = M[(size_t)j * TS + D * R + a];
+}
+
+// ---------------------------------------------------------------------------------------------
+// Boundary-pose exchange helpers (ref: PGOAgent::getSharedPoseDict src/PGOAgent.cpp:95-105,
+// PGOAgent::constructGMatrix :783-859)
+// ---------------------------------------------------------------------------------------------
+__global__ void k_pack_tiles(int ts, int count, const int *__restrict__ pose, const double *__restrict__ X,
+                             double *__restrict__ out) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= count * ts) return;
+  const int s = t / ts, e = t - s * ts;
+  out[t] = X[(size_t)pose[s] * ts + e];
+}
+
+// One thread per (pose with shared edges, element): walks that pose's edges in a fixed order
+// (deterministic sum).  outgoing: G_p += -(X_j Om) T^T ; incoming: G_p += -(X_i T) Om.
+template <int R, int DH>
+__global__ void k_build_G(int nposes, const int *__restrict__ pose_ids, const int *__restrict__ pose_ptr,
+                          const int *__restrict__ edge_slot, const int *__restrict__ edge_out,
+                          const double *__restrict__ edge_T, const double *__restrict__ edge_om,
+                          const double *__restrict__ gathered, double *__restrict__ G) {
+  constexpr int TS = R * DH;
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= nposes * TS) return;
+  const int pi = t / TS, e = t - pi * TS;
+  const int c = e / R, a = e - c * R;          // element (a, c) of the tile
+  double acc = 0.0;
+  for (int k = pose_ptr[pi]; k < pose_ptr[pi + 1]; ++k) {
+    const double *Xn = gathered + (size_t)edge_slot[k] * TS;     // neighbour tile
+    const double *T = edge_T + (size_t)k * DH * DH;              // row-major DH x DH
+    const double *om = edge_om + (size_t)k * DH;
+    double s = 0.0;
+    if (edge_out[k]) {        // L[a,c] = -sum_q Xn[a,q] om[q] T[c][q]
+#pragma unroll
+      for (int q = 0; q < DH; ++q) s = fma(Xn[q * R + a] * om[q], T[c * DH + q], s);
+    } else {                  // L[a,c] = -sum_q Xn[a,q] T[q][c] om[c]
+#pragma unroll
+      for (int q = 0; q < DH; ++q) s = fma(Xn[q * R + a], T[q * DH + c], s);
+      s *= om[c];
+    }
+    acc -= s;
+  }
+  G[(size_t)pose_ids[pi] * TS + e] = acc;
+}
+
+// ---------------------------------------------------------------------------------------------
+// launchers
+// ---------------------------------------------------------------------------------------------
+template <int R, int DH> static cudaError_t launch_optimize_t(const KParams &kp, cudaStream_t stream) {
+  const size_t smem = ((OPT_THREADS / 32) * NRED + NRED + 1024 * R) * sizeof(double);
+  static bool attr_set[64] = {};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 64 || !attr_set[dev]) {
+    cudaError_t e = cudaFuncSetAttribute(k_optimize<R, DH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    if (dev >= 0 && dev < 64) attr_set[dev] = true;
+  }
+  void *args[] = {(void *)&kp};
+  return cudaLaunchCooperativeKernel((void *)k_optimize<R, DH>, dim3(kp.grid), dim3(OPT_THREADS), args, smem, stream);
+}
+
+template <int R, int DH> static int max_grid_t(int device) {
+  const size_t smem = ((OPT_THREADS / 32) * NRED + NRED + 1024 * R) * sizeof(double);
+  cudaFuncSetAttribute(k_optimize<R, DH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  int per_sm = 0, sms = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_optimize<R, DH>, OPT_THREADS, smem) != cudaSuccess) return 0;
+  if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device) != cudaSuccess) return 0;
+  return per_sm > 0 ? sms : 0;      // one CTA per SM
+}
+
+#define DPGO_DISPATCH(R_, DH_, ...)                                    \
+  do {                                                                   \
+    if ((DH_) == 4) {                                                    \
+      switch (R_) {                                                      \
+        case 3: { constexpr int R = 3, DH = 4; __VA_ARGS__; } break;     \
+        case 4: { constexpr int R = 4, DH = 4; __VA_ARGS__; } break;     \
+        case 5: { constexpr int R = 5, DH = 4; __VA_ARGS__; } break;     \
+        default: break;                                                  \
+      }                                                                  \
+    } else if ((DH_) == 3) {                                             \
+      switch (R_) {                                                      \
+        case 2: { constexpr int R = 2, DH = 3; __VA_ARGS__; } break;     \
+        case 3: { constexpr int R = 3, DH = 3; __VA_ARGS__; } break;     \
+        case 5: { constexpr int R = 5, DH = 3; __VA_ARGS__; } break;     \
+        default: break;                                                  \
+      }                                                                  \
+    }                                                                    \
+  } while (0)
+
+cudaError_t launch_optimize(int r, int dh, const KParams &kp, cudaStream_t stream) {
+  cudaError_t e = cudaErrorInvalidValue;
+  DPGO_DISPATCH(r, dh, e = (launch_optimize_t<R, DH>(kp, stream)));
+  return e;
+}
+
+int optimize_max_grid(int r, int dh, int device) {
+  int g = 0;
+  DPGO_DISPATCH(r, dh, g = (max_grid_t<R, DH>(device)));
+  return g;
+}
+
+cudaError_t launch_spmv(int r, int dh, int n, const int *rowptr, const int *bcol, const double *bval,
+                        const double *X, const double *G, double *out, cudaStream_t stream) {
+  bool ok = false;
+  DPGO_DISPATCH(r, dh, {
+    constexpr int SG = SubGroup<R>::SG;
+    const int per_block = SPMV_THREADS / SG;
+    const int blocks = (n + per_block - 1) / per_block;
+    k_spmv<R, DH><<<blocks, SPMV_THREADS, 0, stream>>>(n, rowptr, bcol, bval, X, G, out);
+    ok = true;
+  });
+  if (!ok) return cudaErrorInvalidValue;
+  return cudaGetLastError();
+}
+
+cudaError_t launch_stiefel_project(int r, int dh, int n, const double *M, double *out, cudaStream_t stream) {
+  bool ok = false;
+  DPGO_DISPATCH(r, dh, {
+    k_stiefel_project<R, DH><<<(n + 127) / 128, 128, 0, stream>>>(n, M, out);
+    ok = true;
+  });
+  if (!ok) return cudaErrorInvalidValue;
+  return cudaGetLastError();
+}
+
+cudaError_t launch_pack_tiles(int ts, int count, const int *pose, const double *X, double *out, cudaStream_t stream) {
+  if (count <= 0) return cudaSuccess;
+  const int total = count * ts;
+  k_pack_tiles<<<(total + 255) / 256, 256, 0, stream>>>(ts, count, pose, X, out);
+  return cudaGetLastError();
+}
+
+
+__global__ void k_scatter_dense(const int *__restrict__ row, const int *__restrict__ col, const double *__restrict__ val,
+                                int64_t count, double *__restrict__ A, int N) {
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < count) A[(size_t)row[t] + (size_t)N * col[t]] = val[t];
+}
+
+cudaError_t launch_scatter_dense(const int *row, const int *col, const double *val, int64_t count, double *A, int N,
+                                 cudaStream_t stream) {
+  if (count <= 0) return cudaSuccess;
+  k_scatter_dense<<<(unsigned)((count + 255) / 256), 256, 0, stream>>>(row, col, val, count, A, N);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_build_G(int r, int dh, int nposes, const int *pose_ids, const int *pose_ptr, const int *edge_slot,
+                           const int *edge_out, const double *edge_T, const double *edge_om, const double *gathered,
+                           double *G, cudaStream_t stream) {
+  if (nposes <= 0) return cudaSuccess;
+  bool ok = false;
+  DPGO_DISPATCH(r, dh, {
+    const int total = nposes * R * DH;
+    k_build_G<R, DH><<<(total + 127) / 128, 128, 0, stream>>>(nposes, pose_ids, pose_ptr, edge_slot, edge_out, edge_T,
+                                                              edge_om, gathered, G);
+    ok = true;
+  });
+  if (!ok) return cudaErrorInvalidValue;
+  return cudaGetLastError();
+}
+
+}  // namespace dpgo

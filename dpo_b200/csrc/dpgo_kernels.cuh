@@ -1,0 +1,71 @@
+// dpgo_kernels.cuh -- kernel-side parameter block shared by dpgo_kernels.cu and dpgo_capi.cu
+#pragma once
+#include <stdint.h>
+#include "../../include/dpgo_b200.h"
+
+namespace dpgo {
+
+// work vectors, each r x (d+1)n fp64 in HBM
+enum VecId {
+  V_X0 = 0, V_X1,        // iterate double buffer (X0 is the externally visible one)
+  V_EG0, V_EG1,          // Euclidean gradient at X0 / X1
+  V_RG0, V_RG1,          // Riemannian gradient
+  V_Z00, V_Z01,          // preconditioned gradient M^-1 g at X0 / X1
+  V_ETA, V_RES, V_Z,     // tCG: step, residual, preconditioned residual
+  V_D0, V_D1,            // tCG: search direction double buffer
+  V_HD,                  // H[delta]
+  V_T,                   // dense-preconditioner scratch
+  V_XIN,                 // copy of the input iterate (relative change)
+  V_AUX,                 // operand of the single-operation entry points
+  V_COUNT
+};
+
+enum OpCode {
+  OP_OPTIMIZE = 0,   // full RTR / RGD call
+  OP_EVAL = 1,       // f, EG, RG, |RG| at X0
+  OP_RHESS = 2,      // HD = Hess f(X0)[AUX]
+  OP_PRECON = 3,     // Z  = P_X0( M^-1 AUX )
+  OP_RETRACT = 4,    // X1 = R_X0(AUX)
+};
+
+constexpr int NRED = 4;            // scalars reduced per phase
+constexpr int OPT_THREADS = 512;   // persistent kernel block size
+
+struct KParams {
+  int n;                 // poses
+  int N;                 // (d+1) n
+  int grid;              // CTAs of the persistent kernel
+  int op;
+  const int *rowptr;     // n+1
+  const int *bcol;       // nb
+  const double *bval;    // nb*16
+  const double *dinv;    // n*16   block-Jacobi inverse blocks, may be null
+  const double *pinv;    // N*N    dense inverse of Q+0.1I, may be null
+  const int *cta_rows;   // grid+1 balanced row partition
+  const double *G;       // linear term r x N
+  double *v[V_COUNT];
+  double *S[2];          // n*9   sym(Y^T EG_Y) per pose at X0 / X1
+  double *partials;      // 2 * grid * NRED
+  unsigned *bar_counter;
+  unsigned *bar_epoch;
+  dpgo_opt_params_t prm;
+  dpgo_opt_result_t *result;   // device copy of the result record
+};
+
+// launchers (dpgo_kernels.cu)
+cudaError_t launch_optimize(int r, int dh, const KParams &kp, cudaStream_t stream);
+cudaError_t launch_spmv(int r, int dh, int n, const int *rowptr, const int *bcol, const double *bval,
+                        const double *X, const double *G, double *out, cudaStream_t stream);
+int optimize_max_grid(int r, int dh, int device);   // co-resident CTA count for the persistent kernel
+cudaError_t launch_stiefel_project(int r, int dh, int n, const double *M, double *out, cudaStream_t stream);
+cudaError_t launch_pack_tiles(int ts, int count, const int *pose, const double *X, double *out, cudaStream_t stream);
+cudaError_t launch_build_G(int r, int dh, int nposes, const int *pose_ids, const int *pose_ptr, const int *edge_slot,
+                           const int *edge_out, const double *edge_T, const double *edge_om, const double *gathered,
+                           double *G, cudaStream_t stream);
+cudaError_t launch_scatter_dense(const int *row, const int *col, const double *val, int64_t count, double *A, int N,
+                                 cudaStream_t stream);
+
+// dense SPD inverse in place (dense_inverse.cu); A is N x N, ld = N, symmetric positive definite
+cudaError_t dense_spd_inverse(double *A, int N, cudaStream_t stream);
+
+}  // namespace dpgo

@@ -1,0 +1,201 @@
+/*
+ * dpgo_b200.h -- C ABI of the B200-native pose-graph-optimisation hot path.
+ *
+ * This is the drop-in boundary: every entry point replaces one piece of the reference's
+ * (tjcunhao/dpo, fork of mit-acl/dpgo) C++ interface for the per-iteration path.  The
+ * reference has no C ABI of its own; the C++ mirror under include/DPGO/ (same class names and
+ * signatures as the reference) and the Python mirror dpo_b200/ are thin hosts over this file.
+ * "ref:" comments cite the reference interface each function stands in for (paths relative
+ * to the reference root).
+ *
+ * Conventions
+ *   - plain pointers and sizes only; no C++/torch types; all functions return a status code
+ *     (DPGO_OK == 0) and never throw or abort.  dpgo_last_error() gives a thread-local message.
+ *   - dense arrays are COLUMN-MAJOR r x (d+1)n doubles; pose i is the contiguous r x (d+1)
+ *     tile at columns [(d+1)i, (d+1)(i+1)) (layout pinned by ref tests/testEigenMap.cpp:12-36).
+ *   - "host" pointers are caller-owned CPU memory (the library copies in/out);
+ *     "dev" pointers are CUDA device memory on the problem's device.
+ *   - one opaque handle <-> one GPU <-> one CUDA stream; a handle is used by one thread at a
+ *     time (ref: a QuadraticProblem is used by one thread at a time, src/PGOAgent.cpp:676-682).
+ *   - all arithmetic is fp64.  There is NO CPU fallback: without a usable CUDA device
+ *     dpgo_problem_create() fails with DPGO_ERR_NO_DEVICE.
+ */
+#ifndef DPGO_B200_H
+#define DPGO_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DPGO_B200_ABI_VERSION 1
+
+#if defined(__GNUC__)
+#define DPGO_API __attribute__((visibility("default")))
+#else
+#define DPGO_API
+#endif
+
+/* ---- status codes ------------------------------------------------------------------ */
+enum {
+  DPGO_OK = 0,
+  DPGO_ERR_INVALID_ARG = 1, /* shape / pointer / range violation (ref: assert() on shapes,
+                               src/QuadraticProblem.cpp:32-33,51-52) */
+  DPGO_ERR_NO_DEVICE = 2,   /* no CUDA device / device index out of range */
+  DPGO_ERR_CUDA = 3,        /* a CUDA runtime call or kernel failed */
+  DPGO_ERR_STATE = 4,       /* call order violation (e.g. optimise before set_Q) */
+  DPGO_ERR_UNSUPPORTED = 5, /* d not in {2,3}; r outside the compiled set (d=3: 3..5, d=2: 2,3,5); N too large for
+                               the dense preconditioner */
+  DPGO_ERR_ALLOC = 6
+};
+
+/* ---- enums mirrored from the reference ----------------------------------------------- */
+/* ref: include/DPGO/DPGO_types.h:29-35 (ROPTALG) */
+enum { DPGO_ALG_RTR = 0, DPGO_ALG_RGD = 1 };
+
+/* Preconditioner used inside truncated CG.
+ * ref: src/QuadraticProblem.cpp:31-42,75-87: exact solve with Q + 0.1 I (CHOLMOD) followed by
+ * tangent projection.  DENSE_EXACT applies the same operator through a dense inverse resident
+ * in HBM (per-iteration trace parity with the reference); BLOCK_JACOBI is the SpMV-only
+ * throughput mode (same fixed points, different inner iterates); NONE is projection only. */
+enum { DPGO_PRECOND_NONE = 0, DPGO_PRECOND_BLOCK_JACOBI = 1, DPGO_PRECOND_DENSE_EXACT = 2 };
+
+/* ref: ROPTLIB tCGstatusSet as recorded by src/QuadraticOptimizer.cpp:115 */
+enum {
+  DPGO_TCG_NEGCURVTURE = 0, DPGO_TCG_EXCREGION = 1, DPGO_TCG_LCON = 2, DPGO_TCG_SCON = 3,
+  DPGO_TCG_MAXITER = 4, DPGO_TCG_NOT_RUN = -1
+};
+
+typedef struct dpgo_problem dpgo_problem_t; /* opaque: QuadraticProblem + manifold + device state */
+
+/* Solver knobs.  ref: include/DPGO/QuadraticOptimizer.h:36-70 setters; defaults
+ * src/QuadraticOptimizer.cpp:20-29 (RTR, step 1e-3, 1 iteration, tol 1e-2, radius 10, 50 inner). */
+typedef struct dpgo_opt_params {
+  int32_t algorithm;          /* DPGO_ALG_* */
+  int32_t tr_iterations;      /* setTrustRegionIterations */
+  int32_t tr_max_inner;       /* setTrustRegionMaxInnerIterations */
+  int32_t precond;            /* DPGO_PRECOND_* (must have been prepared by set_Q) */
+  double rgd_stepsize;        /* setGradientDescentStepsize */
+  double tr_tolerance;        /* setTrustRegionTolerance */
+  double tr_initial_radius;   /* setTrustRegionInitialRadius */
+} dpgo_opt_params_t;
+
+/* ref: include/DPGO/DPGO_types.h:40-59 (ROPTResult) + bookkeeping counters. */
+typedef struct dpgo_opt_result {
+  int32_t success;
+  int32_t tcg_status;        /* status of the last tCG solve */
+  int32_t tcg_iterations;    /* inner iterations summed over all attempts */
+  int32_t outer_iterations;  /* RTR attempts executed (accepted + rejected) */
+  int32_t rejections;        /* rejected attempts */
+  int32_t spmv_passes;       /* passes over Q executed inside the call */
+  double f_init, gradnorm_init, f_opt, gradnorm_opt, relative_change, elapsed_ms;
+} dpgo_opt_result_t;
+
+/* ---- library / device ---------------------------------------------------------------- */
+DPGO_API int dpgo_abi_version(void);
+DPGO_API const char *dpgo_last_error(void);
+DPGO_API int dpgo_device_count(int *count);
+DPGO_API void dpgo_opt_params_default(dpgo_opt_params_t *p);
+
+/* ---- problem lifetime.  ref: QuadraticProblem ctor/dtor, include/DPGO/QuadraticProblem.h:33-35 */
+DPGO_API int dpgo_problem_create(int n, int d, int r, int device, dpgo_problem_t **out);
+DPGO_API int dpgo_problem_destroy(dpgo_problem_t *p);
+/* Run the handle's work on a caller-provided cudaStream_t (e.g. torch's current stream). NULL
+ * restores the handle's own stream. */
+DPGO_API int dpgo_problem_set_stream(dpgo_problem_t *p, void *cuda_stream);
+DPGO_API int dpgo_problem_sync(dpgo_problem_t *p);
+DPGO_API int dpgo_problem_dims(const dpgo_problem_t *p, int *n, int *d, int *r, int64_t *num_blocks);
+
+/* ---- cost matrices ------------------------------------------------------------------- */
+/* ref: QuadraticProblem::setQ(const SparseMatrix&), src/QuadraticProblem.cpp:31-42.
+ * Q is the scalar row-major CSR exactly as Eigen::SparseMatrix<double,RowMajor> exposes it
+ * (outerIndexPtr / innerIndexPtr / valuePtr), (d+1)n x (d+1)n, symmetric.  The library converts
+ * it to (d+1)x(d+1) block-CSR in HBM and prepares the preconditioners named in precond_mask
+ * (bit i = DPGO_PRECOND_i). */
+DPGO_API int dpgo_problem_set_Q_csr(dpgo_problem_t *p, int nrows, const int32_t *rowptr, const int32_t *colind,
+                           const double *values, unsigned precond_mask);
+/* Same from block triplets: nb blocks, block k at (brow[k], bcol[k]) holds the (d+1)x(d+1)
+ * sub-matrix Q[(d+1)brow.., (d+1)bcol..] row-major in blocks[k*(d+1)^2 ..]; duplicates are summed
+ * (what ref constructConnectionLaplacianSE / PGOAgent::constructQMatrix produce,
+ * src/DPGO_utils.cpp:264-271, src/PGOAgent.cpp:720-781). */
+DPGO_API int dpgo_problem_set_Q_blocks(dpgo_problem_t *p, int64_t nb, const int32_t *brow, const int32_t *bcol,
+                              const double *blocks, unsigned precond_mask);
+/* ref: QuadraticProblem::setG, src/QuadraticProblem.cpp:44-48.  Dense r x (d+1)n column-major,
+ * or the reference's sparse form (row-major CSR with r rows).  NULL / nnz == 0 clears G. */
+DPGO_API int dpgo_problem_set_G_dense(dpgo_problem_t *p, const double *G_host);
+DPGO_API int dpgo_problem_set_G_csr(dpgo_problem_t *p, const int32_t *rowptr, const int32_t *colind,
+                           const double *values);
+
+/* ---- evaluation (host in / host out) --------------------------------------------------- */
+/* ref: QuadraticProblem::f, src/QuadraticProblem.cpp:50-60 */
+DPGO_API int dpgo_problem_f(dpgo_problem_t *p, const double *X_host, double *f_out);
+/* ref: QuadraticProblem::EucGrad, :62-66  (Out = X Q + G) */
+DPGO_API int dpgo_problem_egrad(dpgo_problem_t *p, const double *X_host, double *out_host);
+/* ref: QuadraticProblem::EucHessianEta, :68-73  (Out = V Q) */
+DPGO_API int dpgo_problem_ehess(dpgo_problem_t *p, const double *V_host, double *out_host);
+/* ref: QuadraticProblem::RieGrad / RieGradNorm, :89-101.  Either output may be NULL. */
+DPGO_API int dpgo_problem_rgrad(dpgo_problem_t *p, const double *X_host, double *out_host, double *norm_out);
+/* f, Riemannian gradient norm in ONE pass over Q (what optimize() needs before/after) */
+DPGO_API int dpgo_problem_f_rgradnorm(dpgo_problem_t *p, const double *X_host, double *f_out, double *norm_out);
+/* Riemannian Hessian-vector product at X: ROPTLIB Problem::HessianEta = EucHessianEta +
+ * Stiefel::EucHvToHv + projection (call site src/QuadraticOptimizer.cpp:76-119). */
+DPGO_API int dpgo_problem_rhess(dpgo_problem_t *p, const double *X_host, const double *V_host, double *out_host);
+/* ref: QuadraticProblem::PreConditioner, :75-87 */
+DPGO_API int dpgo_problem_precon(dpgo_problem_t *p, int precond, const double *X_host, const double *V_host,
+                        double *out_host);
+
+/* ---- manifold (St(d,r) x R^r)^n ------------------------------------------------------- */
+/* ROPTLIB ProductManifold::Projection (tangent projection at X), call sites
+ * src/QuadraticProblem.cpp:82,95, src/QuadraticOptimizer.cpp:139 */
+DPGO_API int dpgo_manifold_tangent_project(dpgo_problem_t *p, const double *X_host, const double *Z_host,
+                                  double *out_host);
+/* ROPTLIB ProductManifold::Retraction (QF per pose), src/QuadraticOptimizer.cpp:146 */
+DPGO_API int dpgo_manifold_retract(dpgo_problem_t *p, const double *X_host, const double *eta_host,
+                          double *out_host);
+/* ref: LiftedSEManifold::project, src/manifold/LiftedSEManifold.cpp:34-45 (polar factor per pose) */
+DPGO_API int dpgo_manifold_project(dpgo_problem_t *p, const double *M_host, double *out_host);
+
+/* ---- optimiser ------------------------------------------------------------------------ */
+/* ref: QuadraticOptimizer::optimize(const Matrix&), src/QuadraticOptimizer.cpp:34-59: one
+ * RTR (Riemannian trust region, truncated-CG inner solve) or RGD call, the whole loop on the
+ * device in one persistent kernel; host sees only X_out and the result record. */
+DPGO_API int dpgo_optimize(dpgo_problem_t *p, const dpgo_opt_params_t *params, const double *X_in_host,
+                  double *X_out_host, dpgo_opt_result_t *result);
+
+/* ---- device-resident path (iterate lives in HBM between calls) --------------------------- */
+DPGO_API int dpgo_problem_upload_X(dpgo_problem_t *p, const double *X_host);
+DPGO_API int dpgo_problem_download_X(dpgo_problem_t *p, double *X_host);
+DPGO_API int dpgo_problem_device_X(dpgo_problem_t *p, double **X_dev);     /* r x (d+1)n, read/write */
+DPGO_API int dpgo_problem_device_G(dpgo_problem_t *p, double **G_dev);
+/* optimise the resident iterate in place; asynchronous on the handle's stream */
+DPGO_API int dpgo_optimize_resident_async(dpgo_problem_t *p, const dpgo_opt_params_t *params);
+/* wait for the last async optimise and fetch its result record */
+DPGO_API int dpgo_optimize_result(dpgo_problem_t *p, dpgo_opt_result_t *result);
+/* the Q.X product kernel alone on device buffers (the roofline kernel): Out = X Q (+ G) */
+DPGO_API int dpgo_spmv_device(dpgo_problem_t *p, const double *X_dev, double *out_dev, int add_G);
+DPGO_API int64_t dpgo_spmv_algorithmic_bytes(const dpgo_problem_t *p, int add_G);
+
+/* ---- boundary-pose exchange (multi-agent, one agent per GPU) ----------------------------- */
+/* ref: PGOAgent::getSharedPoseDict, src/PGOAgent.cpp:95-105: register which local poses are
+ * public; pack gathers their r x (d+1) tiles into a contiguous device buffer (the NCCL
+ * all-gather send buffer), slot s <- pose public_pose[s]. */
+DPGO_API int dpgo_agent_set_public_poses(dpgo_problem_t *p, int num_public, const int32_t *public_pose);
+DPGO_API int dpgo_agent_pack_public(dpgo_problem_t *p, double *send_dev);
+/* ref: PGOAgent::constructGMatrix, src/PGOAgent.cpp:783-859.  Shared edge e touches local pose
+ * local_pose[e]; its neighbour pose is tile nbr_slot[e] of the gathered buffer; outgoing[e]!=0
+ * means this agent owns the edge tail (G_p1 += -X_j Om T^T) else the head (G_p2 += -X_i T Om).
+ * T is (d+1)x(d+1) row-major per edge, omega the (d+1) diagonal weights (kappa..,tau)*weight. */
+DPGO_API int dpgo_agent_set_shared_edges(dpgo_problem_t *p, int num_edges, const int32_t *local_pose,
+                                const int32_t *nbr_slot, const int32_t *outgoing, const double *T,
+                                const double *omega);
+/* rebuild G in HBM from the gathered neighbour tiles (deterministic: edges grouped per pose) */
+DPGO_API int dpgo_agent_build_G(dpgo_problem_t *p, const double *gathered_dev, int64_t num_slots);
+/* per-agent Riemannian gradient norm / cost of the resident iterate (greedy selection input) */
+DPGO_API int dpgo_agent_f_rgradnorm_resident(dpgo_problem_t *p, double *f_out, double *norm_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DPGO_B200_H */
