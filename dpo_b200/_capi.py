@@ -33,9 +33,11 @@ class OptParams(C.Structure):
 
 class OptResult(C.Structure):
     _fields_ = [("success", C.c_int32), ("tcg_status", C.c_int32), ("tcg_iterations", C.c_int32),
-                ("outer_iterations", C.c_int32), ("rejections", C.c_int32), ("spmv_passes", C.c_int32),
+                ("outer_iterations", C.c_int32), ("rejections", C.c_int32), ("spmv_passes", C.c_int32), ("precond_applies", C.c_int32),
+                ("reserved0", C.c_int32),
                 ("f_init", C.c_double), ("gradnorm_init", C.c_double), ("f_opt", C.c_double),
-                ("gradnorm_opt", C.c_double), ("relative_change", C.c_double), ("elapsed_ms", C.c_double)]
+                ("gradnorm_opt", C.c_double), ("relative_change", C.c_double), ("elapsed_ms", C.c_double),
+                ("quad_init", C.c_double), ("lin_init", C.c_double)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}
@@ -74,6 +76,7 @@ SIGNATURES = {
     "dpgo_optimize": (C.c_int, [_vp, C.POINTER(OptParams), _dp, _dp, C.POINTER(OptResult)]),
     "dpgo_problem_upload_X": (C.c_int, [_vp, _dp]),
     "dpgo_problem_download_X": (C.c_int, [_vp, _dp]),
+    "dpgo_problem_copy_X_from_device": (C.c_int, [_vp, _vp]),
     "dpgo_problem_device_X": (C.c_int, [_vp, C.POINTER(_vp)]),
     "dpgo_problem_device_G": (C.c_int, [_vp, C.POINTER(_vp)]),
     "dpgo_optimize_resident_async": (C.c_int, [_vp, C.POINTER(OptParams)]),

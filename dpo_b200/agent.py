@@ -1,0 +1,503 @@
+"""PGOAgent mirror + the multi-GPU runner (one agent per GPU, boundary poses over one all-gather).
+
+`PGOAgent` keeps the reference's public interface for the parts on / next to the hot path
+(ref include/DPGO/PGOAgent.h:209-490, src/PGOAgent.cpp): setPoseGraph, setX/getX, getSharedPoseDict,
+updateNeighborPoses, iterate, getNeighbors, getTrajectoryInLocalFrame, localPoseGraphOptimization.
+Host bookkeeping stays on the host, every numeric step runs in libdpgo_b200.so.
+
+`ExchangePlan` + `DistributedPGO` are the B200-native replacement of the reference's in-process
+"network" (examples/MultiRobotExample.cpp:245-256): public poses are packed on the device,
+exchanged with ONE all-gather per round (NCCL over NVLink when the tensors are CUDA), and G is
+rebuilt on the device from the gathered tiles (ref PGOAgent::constructGMatrix, src/PGOAgent.cpp:783-859).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass, field
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import numpy as np
+
+from . import _capi as capi
+from . import posegraph as pg
+from .posegraph import EdgeSet
+from .problem import QuadraticOptimizer, QuadraticProblem, ROPTALG
+
+PoseID = Tuple[int, int]
+
+
+@dataclass
+class PGOAgentParameters:
+    """ref: include/DPGO/PGOAgent.h:59-136 (fields on the hot path; robust-cost knobs are out of scope)."""
+    d: int
+    r: int
+    numRobots: int = 1
+    algorithm: int = ROPTALG.RTR
+    acceleration: bool = False
+    restartInterval: int = 30
+    maxNumIters: int = 500
+    relChangeTol: float = 5e-3
+    verbose: bool = False
+    preconditioner: int = capi.PRECOND_DENSE_EXACT      # B200 extension (reference operator by default)
+    device: int = 0
+
+
+class PGOAgentState:
+    WAIT_FOR_DATA, WAIT_FOR_INITIALIZATION, INITIALIZED = 0, 1, 2
+
+
+# ---------------------------------------------------------------------------------------------------
+# partitioning (ref examples/MultiRobotExample.cpp:63-151)
+# ---------------------------------------------------------------------------------------------------
+def contiguous_owner(n: int, k: int) -> np.ndarray:
+    """Pose -> agent, contiguous ranges, last agent takes the remainder (ref :95-109)."""
+    per = n // k
+    if per <= 0:
+        raise ValueError("More robots than total number of poses! Decrease the number of robots")
+    return np.minimum(np.arange(n) // per, k - 1).astype(np.int64)
+
+
+def partition_edges(edges: EdgeSet, owner: np.ndarray, k: int):
+    """Split a global edge list into per-agent (odometry, private, shared) sets with local pose ids
+    (ref :115-151).  Returns (parts, counts, global_index_of[a])."""
+    n = owner.shape[0]
+    counts = np.bincount(owner, minlength=k).astype(np.int64)
+    local = np.empty(n, dtype=np.int64)
+    glob = []
+    for a in range(k):
+        idx = np.flatnonzero(owner == a)
+        local[idx] = np.arange(idx.shape[0])
+        glob.append(idx)
+    a1, a2 = owner[edges.p1], owner[edges.p2]
+    re = EdgeSet(edges.d, a1, a2, local[edges.p1], local[edges.p2], edges.R, edges.t, edges.kappa, edges.tau,
+                 edges.weight)
+    same = a1 == a2
+    odo = edges.p1 + 1 == edges.p2                     # ref :134 tests GLOBAL ids
+    parts = []
+    for a in range(k):
+        mine = same & (a1 == a)
+        parts.append((re.take(np.flatnonzero(mine & odo)), re.take(np.flatnonzero(mine & ~odo)),
+                      re.take(np.flatnonzero(~same & ((a1 == a) | (a2 == a))))))
+    return parts, counts, glob
+
+
+# ---------------------------------------------------------------------------------------------------
+# exchange plan: who publishes what, where it lands in the gathered buffer
+# ---------------------------------------------------------------------------------------------------
+class ExchangePlan:
+    """Static tables of the boundary-pose exchange for k agents.
+
+    public[a]   sorted local ids of agent a's public poses (ref localSharedPoseIDs, src/PGOAgent.cpp:236-245)
+    pmax        padded slot count per agent (all-gather needs equal counts)
+    slot(b, q)  = b * pmax + position of q in public[b]
+    edge tables for agent a: local pose, neighbour slot, outgoing flag, T (row-major), omega
+    """
+
+    def __init__(self, shared: Sequence[EdgeSet], k: int):
+        self.k = k
+        self.public: List[np.ndarray] = []
+        for a in range(k):
+            s = shared[a]
+            mine = np.where(s.r1 == a, s.p1, s.p2)
+            self.public.append(np.unique(mine).astype(np.int32))
+        self.pmax = max(1, max(len(p) for p in self.public))
+        self._pos = [{int(q): i for i, q in enumerate(p)} for p in self.public]
+        self.tables = []
+        for a in range(k):
+            s = shared[a]
+            out = (s.r1 == a)
+            local = np.where(out, s.p1, s.p2).astype(np.int32)
+            nbr_agent = np.where(out, s.r2, s.r1)
+            nbr_pose = np.where(out, s.p2, s.p1)
+            slot = np.array([int(b) * self.pmax + self._pos[int(b)][int(q)] for b, q in zip(nbr_agent, nbr_pose)],
+                            dtype=np.int32)
+            self.tables.append(dict(local=local, slot=slot, outgoing=out.astype(np.int32),
+                                    T=np.ascontiguousarray(s.homogeneous()), omega=np.ascontiguousarray(s.omega()),
+                                    neighbors=sorted(set(int(b) for b in nbr_agent))))
+
+    def slot(self, agent: int, local_pose: int) -> int:
+        return agent * self.pmax + self._pos[agent][int(local_pose)]
+
+    def colouring(self) -> List[int]:
+        """Greedy colouring of the agent graph: agents of one colour share no edge, so they may update
+        concurrently with exactly the sequential RBCD semantics (hard part 4)."""
+        colour = [-1] * self.k
+        for a in range(self.k):
+            used = {colour[b] for b in self.tables[a]["neighbors"] if colour[b] >= 0}
+            c = 0
+            while c in used:
+                c += 1
+            colour[a] = c
+        return colour
+
+
+# ---------------------------------------------------------------------------------------------------
+# PGOAgent
+# ---------------------------------------------------------------------------------------------------
+class PGOAgent:
+    def __init__(self, ID: int, params: PGOAgentParameters):
+        self.mID = int(ID)
+        self.mParams = params
+        self.d, self.r, self.n = params.d, params.r, 1
+        self.mState = PGOAgentState.WAIT_FOR_DATA
+        self.mIterationNumber = 0
+        self.mInstanceNumber = 0
+        self.X = np.zeros((self.r, self.d + 1))
+        self.X[:self.d, :self.d] = np.eye(self.d)
+        self.YLift: Optional[np.ndarray] = pg.fixedStiefelVariable(self.d, self.r) if ID == 0 else None
+        self.globalAnchor: Optional[np.ndarray] = None
+        self.mProblem: Optional[QuadraticProblem] = None
+        self.neighborPoseDict: Dict[PoseID, np.ndarray] = {}
+        self.localSharedPoseIDs: List[PoseID] = []
+        self.neighborSharedPoseIDs: set = set()
+        self.neighborRobotIDs: List[int] = []
+        self.relativeChange = 0.0
+        self.readyToTerminate = False
+        self.lastResult = None
+        self.TLocalInit: Optional[np.ndarray] = None
+
+    # -- getters (ref .h:237-262) --
+    def getID(self): return self.mID
+    def num_poses(self): return self.n
+    def dimension(self): return self.d
+    def relaxation_rank(self): return self.r
+    def iteration_number(self): return self.mIterationNumber
+    def instance_number(self): return self.mInstanceNumber
+    def getNeighbors(self): return list(self.neighborRobotIDs)
+
+    def getLiftingMatrix(self):
+        assert self.mID == 0
+        return self.YLift
+
+    def setLiftingMatrix(self, M):
+        M = np.asarray(M, dtype=float)
+        assert M.shape == (self.r, self.d)
+        self.YLift = M
+
+    def setGlobalAnchor(self, M):
+        self.globalAnchor = np.asarray(M, dtype=float)
+
+    # -- pose graph (ref src/PGOAgent.cpp:126-195) --
+    def setPoseGraph(self, odometry: EdgeSet, privateLoopClosures: EdgeSet, sharedLoopClosures: EdgeSet,
+                     TInit: Optional[np.ndarray] = None, n: Optional[int] = None) -> None:
+        assert self.mState == PGOAgentState.WAIT_FOR_DATA and self.n == 1
+        if len(odometry) == 0 and n is None:
+            return
+        self.odometry, self.privateLoopClosures, self.sharedLoopClosures = odometry, privateLoopClosures, sharedLoopClosures
+        nn = 1
+        for s in (odometry, privateLoopClosures):
+            if len(s):
+                nn = max(nn, int(max(s.p1.max(), s.p2.max())) + 1)
+        sh = sharedLoopClosures
+        if len(sh):
+            mine = np.where(sh.r1 == self.mID, sh.p1, sh.p2)
+            nn = max(nn, int(mine.max()) + 1)
+            other_r = np.where(sh.r1 == self.mID, sh.r2, sh.r1)
+            other_p = np.where(sh.r1 == self.mID, sh.p2, sh.p1)
+            self.localSharedPoseIDs = [(self.mID, int(q)) for q in np.unique(mine)]
+            self.neighborSharedPoseIDs = {(int(a), int(q)) for a, q in zip(other_r, other_p)}
+            self.neighborRobotIDs = sorted({int(a) for a in other_r})
+        self.n = nn if n is None else int(n)
+        self.mProblem = QuadraticProblem(self.n, self.d, self.r, device=self.mParams.device,
+                                         preconditioners=self._precond_set())
+        self.constructQMatrix()
+        if TInit is not None and np.shape(TInit) == (self.d, (self.d + 1) * self.n):
+            self.TLocalInit = np.array(TInit, dtype=float)
+        else:
+            self.localInitialization()
+        self.mState = PGOAgentState.WAIT_FOR_INITIALIZATION
+        if self.mID == 0 and self.YLift is not None:
+            self.X = self.YLift @ self.TLocalInit
+            self.mState = PGOAgentState.INITIALIZED
+
+    def _precond_set(self):
+        s = {capi.PRECOND_BLOCK_JACOBI}
+        s.add(self.mParams.preconditioner)
+        s.discard(capi.PRECOND_NONE)
+        return tuple(sorted(s))
+
+    def localInitialization(self) -> None:
+        """ref src/PGOAgent.cpp:945-962 (L2 cost -> chordal initialisation on the private edges)."""
+        priv = EdgeSet.join([self.odometry, self.privateLoopClosures])
+        self.TLocalInit = pg.chordalInitialization(self.d, self.n, priv)
+
+    def constructQMatrix(self) -> None:
+        """Private edges' Laplacian + diagonal terms of the shared edges (ref src/PGOAgent.cpp:720-781)."""
+        priv = EdgeSet.join([self.odometry, self.privateLoopClosures])
+        brow, bcol, blocks = pg.connection_laplacian_blocks(priv)
+        sh = self.sharedLoopClosures
+        if len(sh):
+            T, om = sh.homogeneous(), sh.omega()
+            out = sh.r1 == self.mID
+            W = np.zeros_like(T)
+            ar = np.arange(self.d + 1)
+            W[:, ar, ar] = om                                              # incoming: Omega at p2
+            Wout = (T * om[:, None, :]) @ np.transpose(T, (0, 2, 1))       # outgoing: T Omega T^T at p1
+            W[out] = Wout[out]
+            idx = np.where(out, sh.p1, sh.p2).astype(np.int32)
+            brow = np.concatenate([brow, idx])
+            bcol = np.concatenate([bcol, idx])
+            blocks = np.concatenate([blocks, W], axis=0)
+        self.mProblem.setQ_blocks(brow, bcol, blocks)
+
+    def constructGMatrix(self, poseDict: Dict[PoseID, np.ndarray]) -> bool:
+        """Host form (dictionary of neighbour poses), as the reference does it (src/PGOAgent.cpp:783-859)."""
+        sh = self.sharedLoopClosures
+        dh = self.d + 1
+        G = np.zeros((self.r, dh * self.n))
+        T, om = sh.homogeneous(), sh.omega()
+        for k in range(len(sh)):
+            if sh.r1[k] == self.mID:
+                nid = (int(sh.r2[k]), int(sh.p2[k]))
+                if nid not in poseDict:
+                    return False
+                G[:, int(sh.p1[k]) * dh:(int(sh.p1[k]) + 1) * dh] -= (poseDict[nid] * om[k][None, :]) @ T[k].T
+            else:
+                nid = (int(sh.r1[k]), int(sh.p1[k]))
+                if nid not in poseDict:
+                    return False
+                G[:, int(sh.p2[k]) * dh:(int(sh.p2[k]) + 1) * dh] -= (poseDict[nid] @ T[k]) * om[k][None, :]
+        self.mProblem.setG(G)
+        return True
+
+    # -- iterate exchange (ref src/PGOAgent.cpp:55-118, 434-458) --
+    def setX(self, Xin) -> None:
+        Xin = np.asarray(Xin, dtype=float)
+        assert self.mState != PGOAgentState.WAIT_FOR_DATA
+        assert Xin.shape == (self.r, (self.d + 1) * self.n)
+        self.X = Xin.copy()
+        self.mState = PGOAgentState.INITIALIZED
+
+    def getX(self) -> np.ndarray:
+        return self.X.copy()
+
+    def getSharedPose(self, index: int):
+        if self.mState != PGOAgentState.INITIALIZED or index >= self.n:
+            return None
+        dh = self.d + 1
+        return self.X[:, index * dh:(index + 1) * dh].copy()
+
+    def getSharedPoseDict(self) -> Optional[Dict[PoseID, np.ndarray]]:
+        if self.mState != PGOAgentState.INITIALIZED:
+            return None
+        dh = self.d + 1
+        return {pid: self.X[:, pid[1] * dh:(pid[1] + 1) * dh].copy() for pid in self.localSharedPoseIDs}
+
+    def updateNeighborPoses(self, neighborID: int, poseDict: Dict[PoseID, np.ndarray]) -> None:
+        assert neighborID != self.mID
+        for nid, var in poseDict.items():
+            assert nid[0] == neighborID and var.shape == (self.r, self.d + 1)
+            if nid in self.neighborSharedPoseIDs and self.mState == PGOAgentState.INITIALIZED:
+                self.neighborPoseDict[nid] = np.array(var)
+
+    # -- one RBCD step (ref src/PGOAgent.cpp:642-718, updateX :1093-1165) --
+    def iterate(self, doOptimization: bool = True) -> bool:
+        self.mIterationNumber += 1
+        if self.mState != PGOAgentState.INITIALIZED or not doOptimization:
+            return True
+        XPrev = self.X
+        if not self.constructGMatrix(self.neighborPoseDict):
+            if self.mParams.verbose:
+                print(f"Robot {self.mID} could not construct G matrix. Skip update...")
+            self.readyToTerminate = False
+            return False
+        opt = QuadraticOptimizer(self.mProblem)
+        opt.setVerbose(self.mParams.verbose)
+        opt.setAlgorithm(self.mParams.algorithm)
+        opt.setTrustRegionTolerance(1e-2)              # ref :1134-1137
+        opt.setTrustRegionIterations(1)
+        opt.setTrustRegionMaxInnerIterations(10)
+        opt.setTrustRegionInitialRadius(100)
+        opt.setPreconditioner(self.mParams.preconditioner)
+        self.X = np.array(opt.optimize(self.X))
+        self.lastResult = opt.getOptResult()
+        self.relativeChange = float(np.sqrt(np.sum((self.X - XPrev) ** 2) / self.n))
+        self.readyToTerminate = self.relativeChange <= self.mParams.relChangeTol
+        return True
+
+    def localPoseGraphOptimization(self) -> np.ndarray:
+        """ref src/PGOAgent.cpp:964-990: r = d problem on the private edges, RTR 10 outer / 50 inner."""
+        if self.TLocalInit is None:
+            self.localInitialization()
+        priv = EdgeSet.join([self.odometry, self.privateLoopClosures])
+        prob = QuadraticProblem(self.n, self.d, self.d, device=self.mParams.device, preconditioners=self._precond_set())
+        prob.setQ_blocks(*pg.connection_laplacian_blocks(priv))
+        opt = QuadraticOptimizer(prob)
+        opt.setVerbose(self.mParams.verbose)
+        opt.setTrustRegionInitialRadius(10)
+        opt.setTrustRegionIterations(10)
+        opt.setTrustRegionTolerance(1e-1)
+        opt.setTrustRegionMaxInnerIterations(50)
+        opt.setPreconditioner(self.mParams.preconditioner)
+        Topt = np.array(opt.optimize(self.TLocalInit))
+        self.lastResult = opt.getOptResult()
+        prob.close()
+        return Topt
+
+    def getTrajectoryInLocalFrame(self) -> Optional[np.ndarray]:
+        """ref src/PGOAgent.cpp:481-498."""
+        if self.mState != PGOAgentState.INITIALIZED:
+            return None
+        d, dh = self.d, self.d + 1
+        T = self.X[:, :d].T @ self.X
+        t0 = T[:, d].copy()
+        for i in range(self.n):
+            T[:, i * dh:i * dh + d] = pg.projectToRotationGroup(T[:, i * dh:i * dh + d])
+            T[:, i * dh + d] -= t0
+        return T
+
+    # -- device-resident exchange path -----------------------------------------------------------------
+    def attach_exchange(self, plan: ExchangePlan) -> None:
+        lib, h = self.mProblem._lib, self.mProblem._h
+        pub = np.ascontiguousarray(plan.public[self.mID], dtype=np.int32)
+        capi.check(lib.dpgo_agent_set_public_poses(h, len(pub), capi.iptr(pub)))
+        tb = plan.tables[self.mID]
+        capi.check(lib.dpgo_agent_set_shared_edges(h, len(tb["local"]), capi.iptr(tb["local"]), capi.iptr(tb["slot"]),
+                                                   capi.iptr(tb["outgoing"]), capi.dptr(tb["T"]), capi.dptr(tb["omega"])))
+
+    def pack_public(self, send_ptr: int) -> None:
+        capi.check(self.mProblem._lib.dpgo_agent_pack_public(self.mProblem._h, C.c_void_p(send_ptr)))
+
+    def build_G(self, gathered_ptr: int, num_slots: int) -> None:
+        capi.check(self.mProblem._lib.dpgo_agent_build_G(self.mProblem._h, C.c_void_p(gathered_ptr), num_slots))
+
+
+# ---------------------------------------------------------------------------------------------------
+# multi-agent runner
+# ---------------------------------------------------------------------------------------------------
+@dataclass
+class RoundStats:
+    cost: float            # 2 f_central
+    gradnorm: float        # |grad_central|
+    selected: List[int]
+
+
+class DistributedPGO:
+    """One agent per rank (torch.distributed) or all agents in one process (single-GPU simulation).
+
+    schedule = "greedy"   : the reference's synchronous driver (one agent per round, argmax of the per-agent
+                            gradient norm; examples/MultiRobotExample.cpp:229-334) -- parity mode;
+             = "coloured" : all agents of one colour class per round (concurrent, same RBCD semantics);
+             = "parallel" : every agent every round on the neighbours' previous poses.
+    Per round: pack public poses -> ONE all-gather -> device-side G rebuild -> local optimise ->
+    3-scalar all-gather for the central cost / gradient norm / selection.
+    """
+
+    def __init__(self, edges: EdgeSet, n: int, k: int, r: int = 5, algorithm: int = ROPTALG.RTR,
+                 preconditioner: int = capi.PRECOND_DENSE_EXACT, schedule: str = "greedy",
+                 owner: Optional[np.ndarray] = None, X_init: Optional[np.ndarray] = None,
+                 rank: Optional[int] = None, world: Optional[int] = None, device: int = 0, dist=None):
+        import torch
+        self.torch = torch
+        self.dist = dist
+        self.k, self.n, self.r, self.d = k, n, r, edges.d
+        self.rank = rank
+        self.distributed = dist is not None and world is not None and world > 1
+        if self.distributed:
+            assert world == k, "one agent per rank"
+        self.owner = contiguous_owner(n, k) if owner is None else np.asarray(owner, dtype=np.int64)
+        parts, counts, glob = partition_edges(edges, self.owner, k)
+        self.counts, self.glob = counts, glob
+        self.plan = ExchangePlan([p[2] for p in parts], k)
+        self.colour = self.plan.colouring()
+        self.ncolours = max(self.colour) + 1
+        self.schedule = schedule
+        if X_init is None:
+            X_init = pg.fixedStiefelVariable(self.d, r) @ pg.chordalInitialization(self.d, n, edges)
+        self.local_ids = [rank] if self.distributed else list(range(k))
+        self.agents: Dict[int, PGOAgent] = {}
+        dh = self.d + 1
+        self.dev = torch.device("cuda", device)
+        stream = torch.cuda.current_stream(self.dev).cuda_stream
+        for a in self.local_ids:
+            prm = PGOAgentParameters(self.d, r, k, algorithm=algorithm, preconditioner=preconditioner, device=device)
+            ag = PGOAgent(a, prm)
+            ag.mState = PGOAgentState.WAIT_FOR_DATA
+            ag.YLift = None
+            ag.setPoseGraph(*parts[a], TInit=np.zeros((self.d, dh * int(counts[a]))), n=int(counts[a]))
+            cols = (glob[a][:, None] * dh + np.arange(dh)[None, :]).ravel()
+            ag.setX(X_init[:, cols])
+            ag.mProblem.set_stream(stream)
+            ag.mProblem.upload_X(ag.X)
+            ag.attach_exchange(self.plan)
+            ag.opt = QuadraticOptimizer(ag.mProblem)
+            ag.opt.setAlgorithm(algorithm)
+            ag.opt.setTrustRegionTolerance(1e-2)
+            ag.opt.setTrustRegionIterations(1)
+            ag.opt.setTrustRegionMaxInnerIterations(10)
+            ag.opt.setTrustRegionInitialRadius(100)
+            ag.opt.setPreconditioner(preconditioner)
+            self.agents[a] = ag
+        ts = r * dh
+        self.slot_elems = self.plan.pmax * ts
+        self.gathered = torch.zeros(k * self.slot_elems, dtype=torch.float64, device=self.dev)
+        self.send = {a: (self.gathered[a * self.slot_elems:(a + 1) * self.slot_elems] if not self.distributed
+                         else torch.zeros(self.slot_elems, dtype=torch.float64, device=self.dev))
+                     for a in self.local_ids}
+        self.stats_local = torch.zeros(4, dtype=torch.float64, device=self.dev)
+        self.stats_all = torch.zeros(4 * k, dtype=torch.float64, device=self.dev)
+        self.selected = [0]
+        self.round = 0
+
+    # -- the exchange: ONE all-gather of the padded public-pose tiles --------------------------------
+    def exchange(self) -> None:
+        for a in self.local_ids:
+            self.agents[a].pack_public(self.send[a].data_ptr())
+        if self.distributed:
+            self.dist.all_gather_into_tensor(self.gathered, self.send[self.rank])
+        for a in self.local_ids:
+            self.agents[a].build_G(self.gathered.data_ptr(), self.k * self.plan.pmax)
+
+    def _active(self) -> List[int]:
+        if self.schedule == "greedy":
+            return list(self.selected)
+        if self.schedule == "coloured":
+            c = self.round % self.ncolours
+            return [a for a in range(self.k) if self.colour[a] == c]
+        return list(range(self.k))
+
+    def evaluate(self) -> Tuple[float, float, np.ndarray]:
+        """Central cost 2f, |grad|, per-agent gradient norms from per-agent (quad, lin, |g|^2)."""
+        vals = np.zeros((self.k, 4))
+        for a in self.local_ids:
+            res = self.agents[a].opt.problem_stats()
+            vals[a] = res
+        if self.distributed:
+            t = self.torch
+            self.stats_local.copy_(t.from_numpy(vals[self.rank]))
+            self.dist.all_gather_into_tensor(self.stats_all, self.stats_local)
+            vals = self.stats_all.cpu().numpy().reshape(self.k, 4)
+        cost = float(np.sum(vals[:, 0] + vals[:, 1]))          # 2 f_central = sum(<XQ,X> + <X,G>)
+        gn2 = vals[:, 2]
+        return cost, float(np.sqrt(np.sum(gn2))), np.sqrt(gn2)
+
+    def step(self, evaluate: bool = True) -> Optional[RoundStats]:
+        """One round: exchange, active agents optimise, (optionally) exchange again + evaluate + select."""
+        self.exchange()
+        active = self._active()
+        for a in self.local_ids:
+            if a in active:
+                self.agents[a].opt.optimize_resident_async()
+        for a in self.local_ids:
+            if a in active:
+                self.agents[a].lastResult = self.agents[a].opt.fetch_result()
+                self.agents[a].mIterationNumber += 1
+        self.round += 1
+        if not evaluate:
+            return None
+        self.exchange()                                   # fresh neighbour poses for the central gradient
+        cost, gn, per_agent = self.evaluate()
+        if self.schedule == "greedy":
+            cur = self.selected[0]
+            if self.plan.tables[cur]["neighbors"]:
+                self.selected = [int(np.argmax(per_agent))]           # ref :308-325
+        return RoundStats(cost, gn, active)
+
+    def assemble(self) -> np.ndarray:
+        """Gather the full iterate on the host (all local agents; distributed: rank-local block only)."""
+        dh = self.d + 1
+        X = np.zeros((self.r, dh * self.n))
+        for a in self.local_ids:
+            cols = (self.glob[a][:, None] * dh + np.arange(dh)[None, :]).ravel()
+            X[:, cols] = self.agents[a].mProblem.download_X()
+        return X

@@ -654,6 +654,13 @@ int dpgo_problem_download_X(dpgo_problem_t *p, double *X_host) {
   return DPGO_OK;
 }
 
+int dpgo_problem_copy_X_from_device(dpgo_problem_t *p, const double *X_dev) {
+  DPGO_CHECK_HANDLE(p);
+  DPGO_REQUIRE(X_dev, DPGO_ERR_INVALID_ARG, "null X");
+  DPGO_CUDA(cudaMemcpyAsync(p->d_vec[dpgo::V_X0], X_dev, p->vec_bytes(), cudaMemcpyDeviceToDevice, p->stream));
+  return DPGO_OK;
+}
+
 int dpgo_problem_device_X(dpgo_problem_t *p, double **X_dev) {
   DPGO_REQUIRE(p && X_dev, DPGO_ERR_INVALID_ARG, "null argument");
   *X_dev = p->d_vec[dpgo::V_X0];

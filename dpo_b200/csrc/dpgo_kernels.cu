@@ -411,8 +411,9 @@ template <int R, int DH> __global__ void __launch_bounds__(OPT_THREADS, 1) k_opt
   double acc[NRED];
   dpgo_opt_result_t res;
   res.success = 0; res.tcg_status = DPGO_TCG_NOT_RUN; res.tcg_iterations = 0; res.outer_iterations = 0;
-  res.rejections = 0; res.spmv_passes = 0;
+  res.rejections = 0; res.spmv_passes = 0; res.precond_applies = 0; res.reserved0 = 0;
   res.f_init = res.gradnorm_init = res.f_opt = res.gradnorm_opt = res.relative_change = res.elapsed_ms = 0.0;
+  res.quad_init = res.lin_init = 0.0;
 
   int cur = 0;   // which X buffer holds the current iterate
 
@@ -465,6 +466,8 @@ template <int R, int DH> __global__ void __launch_bounds__(OPT_THREADS, 1) k_opt
   double zr0 = acc[3];
   res.f_init = f1;
   res.gradnorm_init = gn;
+  res.quad_init = acc[0];
+  res.lin_init = acc[1];
   res.f_opt = f1;
   res.gradnorm_opt = gn;
 
@@ -516,6 +519,7 @@ template <int R, int DH> __global__ void __launch_bounds__(OPT_THREADS, 1) k_opt
       // -- truncated CG (ROPTLIB SolversTR::tCG_TR; theta = 1, kappa = 0.1, Min_Inner_Iter = 0)
       double z_r = zr0, d_Pd = zr0, e_Pd = 0.0, e_Pe = 0.0;
       const double n0 = gn;
+      res.precond_applies++;                       // z0 = M^-1 g
       double beta = 0.0, tau = 0.0;
       const double *zsrc = kp.v[V_Z00 + cb];
       int pd = 0;                                  // delta_old lives in V_D0 + pd
@@ -558,6 +562,7 @@ template <int R, int DH> __global__ void __launch_bounds__(OPT_THREADS, 1) k_opt
           phase_end(kp, bc, acc);
           zr_new = acc[0];
         }
+        res.precond_applies++;
         beta = zr_new / z_r;
         z_r = zr_new;
         zsrc = kp.v[V_Z];
@@ -645,10 +650,9 @@ __global__ void __launch_bounds__(SPMV_THREADS) k_spmv(int n, const int *__restr
 // ---------------------------------------------------------------------------------------------
 // Stiefel (polar-factor) projection per pose, ref: LiftedSEManifold::project,
 // src/manifold/LiftedSEManifold.cpp:34-45 + projectToStiefelManifold, src/DPGO_utils.cpp:479-485
-// (U V^T of the thin SVD = polar factor).  One thread per pose: polar factor via the
-// eigen-decomposition-free Newton-Schulz-stabilised iteration  Y <- Y (1.5 I - 0.5 Y^T Y) after an
-// initial scaling, switched to the exact form  Y (Y^T Y)^{-1/2}  through a Jacobi eigen-solve of
-// the d x d Gram matrix (cyclic Jacobi, converges quadratically; d <= 3).
+// (U V^T of the thin SVD = polar factor).  One thread per pose: one-sided (Hestenes) Jacobi SVD of
+// the r x d block -- columns are rotated until mutually orthogonal (Y V = U Sigma), which keeps high
+// relative accuracy for ill-conditioned blocks -- then out = U V^T.
 // ---------------------------------------------------------------------------------------------
 template <int R, int DH> __global__ void k_stiefel_project(int n, const double *__restrict__ M, double *__restrict__ out) {
   constexpr int D = DH - 1;
@@ -656,76 +660,65 @@ template <int R, int DH> __global__ void k_stiefel_project(int n, const double *
   const int j = blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= n) return;
   double y[D][R];
+  double V[D][D];
 #pragma unroll
-  for (int c = 0; c < D; ++c)
+  for (int c = 0; c < D; ++c) {
 #pragma unroll
     for (int a = 0; a < R; ++a) y[c][a] = M[(size_t)j * TS + c * R + a];
-  // Gram matrix A = Y^T Y (symmetric D x D)
-  double A[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}}, V[3][3] = {{1, 0, 0}, {0, 1, 0}, {0, 0, 1}};
 #pragma unroll
-  for (int p = 0; p < D; ++p)
-#pragma unroll
-    for (int q = 0; q < D; ++q) {
-      double s = 0;
-#pragma unroll
-      for (int a = 0; a < R; ++a) s = fma(y[p][a], y[q][a], s);
-      A[p][q] = s;
-    }
-  // cyclic Jacobi eigen-decomposition A = V diag(w) V^T
-  for (int sweep = 0; sweep < 12; ++sweep) {
-    double offd = 0;
-#pragma unroll
-    for (int p = 0; p < D; ++p)
-#pragma unroll
-      for (int q = p + 1; q < D; ++q) offd += A[p][q] * A[p][q];
-    if (offd < 1e-300) break;
+    for (int q = 0; q < D; ++q) V[c][q] = (c == q) ? 1.0 : 0.0;     // V[c] = column c of V
+  }
+  for (int sweep = 0; sweep < 30; ++sweep) {
+    bool rotated = false;
 #pragma unroll
     for (int p = 0; p < D; ++p)
 #pragma unroll
       for (int q = p + 1; q < D; ++q) {
-        const double apq = A[p][q];
-        if (apq == 0.0) continue;
-        const double theta = (A[q][q] - A[p][p]) / (2.0 * apq);
-        const double t = (theta >= 0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
-        const double cs = 1.0 / sqrt(t * t + 1.0), sn = t * cs;
+        double alpha = 0, beta = 0, gamma = 0;
 #pragma unroll
-        for (int k = 0; k < D; ++k) {      // A <- A J
-          const double akp = A[k][p], akq = A[k][q];
-          A[k][p] = cs * akp - sn * akq;
-          A[k][q] = sn * akp + cs * akq;
+        for (int a = 0; a < R; ++a) {
+          alpha = fma(y[p][a], y[p][a], alpha);
+          beta = fma(y[q][a], y[q][a], beta);
+          gamma = fma(y[p][a], y[q][a], gamma);
         }
+        if (fabs(gamma) <= 1e-17 * sqrt(alpha * beta) || gamma == 0.0) continue;
+        rotated = true;
+        const double zeta = (beta - alpha) / (2.0 * gamma);
+        const double t = (zeta >= 0 ? 1.0 : -1.0) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
+        const double cs = 1.0 / sqrt(1.0 + t * t), sn = cs * t;
 #pragma unroll
-        for (int k = 0; k < D; ++k) {      // A <- J^T A
-          const double apk = A[p][k], aqk = A[q][k];
-          A[p][k] = cs * apk - sn * aqk;
-          A[q][k] = sn * apk + cs * aqk;
+        for (int a = 0; a < R; ++a) {
+          const double yp = y[p][a], yq = y[q][a];
+          y[p][a] = cs * yp - sn * yq;
+          y[q][a] = sn * yp + cs * yq;
         }
 #pragma unroll
         for (int k = 0; k < D; ++k) {
-          const double vkp = V[k][p], vkq = V[k][q];
-          V[k][p] = cs * vkp - sn * vkq;
-          V[k][q] = sn * vkp + cs * vkq;
+          const double vp = V[p][k], vq = V[q][k];
+          V[p][k] = cs * vp - sn * vq;
+          V[q][k] = sn * vp + cs * vq;
         }
       }
+    if (!rotated) break;
   }
-  // B = V diag(1/sqrt(w)) V^T ; out = Y B
-  double B[3][3];
+  // normalise the rotated columns: U = (Y V) Sigma^-1
 #pragma unroll
-  for (int p = 0; p < D; ++p)
+  for (int c = 0; c < D; ++c) {
+    double s = 0;
 #pragma unroll
-    for (int q = 0; q < D; ++q) {
-      double s = 0;
+    for (int a = 0; a < R; ++a) s = fma(y[c][a], y[c][a], s);
+    const double inv = (s > 0.0) ? 1.0 / sqrt(s) : 0.0;
 #pragma unroll
-      for (int k = 0; k < D; ++k) s += V[p][k] * V[q][k] * (1.0 / sqrt(A[k][k]));
-      B[p][q] = s;
-    }
+    for (int a = 0; a < R; ++a) y[c][a] *= inv;
+  }
+  // out = U V^T : out[a, c] = sum_k U[a,k] V[c,k]   (V[k][c'] holds entry c' of column k)
 #pragma unroll
   for (int c = 0; c < D; ++c)
 #pragma unroll
     for (int a = 0; a < R; ++a) {
       double s = 0;
 #pragma unroll
-      for (int k = 0; k < D; ++k) s = fma(y[k][a], B[k][c], s);
+      for (int k = 0; k < D; ++k) s = fma(y[k][a], V[k][c], s);
       out[(size_t)j * TS + c * R + a] = s;
     }
 #pragma unroll

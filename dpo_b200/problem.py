@@ -196,6 +196,9 @@ class QuadraticProblem:
         capi.check(self._lib.dpgo_problem_download_X(self._h, capi.dptr(out)))
         return out
 
+    def copy_X_from_device(self, src_ptr: int) -> None:
+        capi.check(self._lib.dpgo_problem_copy_X_from_device(self._h, C.c_void_p(src_ptr)))
+
     def device_X_ptr(self) -> int:
         p = C.c_void_p()
         capi.check(self._lib.dpgo_problem_device_X(self._h, C.byref(p)))
@@ -260,10 +263,15 @@ class QuadraticOptimizer:
     def params(self) -> OptParams:
         return self._p
 
-    def optimize(self, Y) -> np.ndarray:
+    def optimize(self, Y, out: Optional[np.ndarray] = None) -> np.ndarray:
+        """One optimize() call, host in / host out.  `out` may be a caller-owned (e.g. pinned) Fortran-ordered
+        (r, (d+1)n) float64 array that receives the result."""
         pr = self.problem
         Yf = pr._in(Y)
-        out = pr._out()
+        if out is None:
+            out = pr._out()
+        elif out.shape != (pr.r, pr.N) or out.dtype != np.float64 or not out.flags.f_contiguous:
+            raise ValueError("out must be a Fortran-contiguous float64 array of shape (r, (d+1)n)")
         capi.check(self._lib.dpgo_optimize(pr._h, C.byref(self._p), capi.dptr(Yf), capi.dptr(out),
                                            C.byref(self.result)))
         if self.verbose:
@@ -278,7 +286,15 @@ class QuadraticOptimizer:
 
     def fetch_result(self) -> OptResult:
         capi.check(self._lib.dpgo_optimize_result(self.problem._h, C.byref(self.result)))
-        return self.result
+        return OptResult.from_buffer_copy(self.result)
 
     def getOptResult(self) -> OptResult:
         return self.result
+
+    def problem_stats(self):
+        """(<XQ,X>, <X,G>, |rgrad|^2, f) of the resident iterate -- per-agent inputs of the central trace."""
+        fo, nrm = C.c_double(), C.c_double()
+        capi.check(self._lib.dpgo_agent_f_rgradnorm_resident(self.problem._h, C.byref(fo), C.byref(nrm)))
+        st = OptResult()
+        capi.check(self._lib.dpgo_optimize_result(self.problem._h, C.byref(st)))
+        return (st.quad_init, st.lin_init, nrm.value ** 2, fo.value)

@@ -90,7 +90,11 @@ typedef struct dpgo_opt_result {
   int32_t outer_iterations;  /* RTR attempts executed (accepted + rejected) */
   int32_t rejections;        /* rejected attempts */
   int32_t spmv_passes;       /* passes over Q executed inside the call */
+  int32_t precond_applies;   /* applications of the tCG preconditioner M^-1 */
+  int32_t reserved0;
   double f_init, gradnorm_init, f_opt, gradnorm_opt, relative_change, elapsed_ms;
+  double quad_init, lin_init; /* <XQ,X> and <X,G> at the input point: f = quad/2 + lin; summed over agents,
+                                 (quad + lin)/2 is the centralised cost (shared-edge cross terms count once) */
 } dpgo_opt_result_t;
 
 /* ---- library / device ---------------------------------------------------------------- */
@@ -167,6 +171,8 @@ DPGO_API int dpgo_optimize(dpgo_problem_t *p, const dpgo_opt_params_t *params, c
 /* ---- device-resident path (iterate lives in HBM between calls) --------------------------- */
 DPGO_API int dpgo_problem_upload_X(dpgo_problem_t *p, const double *X_host);
 DPGO_API int dpgo_problem_download_X(dpgo_problem_t *p, double *X_host);
+/* resident iterate <- device buffer (asynchronous device-to-device copy on the handle's stream) */
+DPGO_API int dpgo_problem_copy_X_from_device(dpgo_problem_t *p, const double *X_dev);
 DPGO_API int dpgo_problem_device_X(dpgo_problem_t *p, double **X_dev);     /* r x (d+1)n, read/write */
 DPGO_API int dpgo_problem_device_G(dpgo_problem_t *p, double **G_dev);
 /* optimise the resident iterate in place; asynchronous on the handle's stream */
