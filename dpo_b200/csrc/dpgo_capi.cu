@@ -50,7 +50,8 @@ struct dpgo_problem {
   bool have_Q = false;
   unsigned precond_mask = 0;
   int *d_rowptr = nullptr, *d_bcol = nullptr, *d_cta_rows = nullptr;
-  double *d_bval = nullptr, *d_dinv = nullptr, *d_pinv = nullptr;
+  double *d_bval = nullptr, *d_dinv = nullptr, *d_pinv = nullptr, *d_dense_part = nullptr;
+  int dense_per = 1;
   // vectors
   double *d_G = nullptr;
   double *d_vec[dpgo::V_COUNT] = {};
@@ -83,6 +84,8 @@ void fill_kparams(const dpgo_problem *p, dpgo::KParams &kp, int op, const dpgo_o
   kp.bval = p->d_bval;
   kp.dinv = p->d_dinv;
   kp.pinv = p->d_pinv;
+  kp.dense_part = p->d_dense_part;
+  kp.dense_per = p->dense_per;
   kp.cta_rows = p->d_cta_rows;
   kp.G = p->d_G;
   for (int i = 0; i < dpgo::V_COUNT; ++i) kp.v[i] = p->d_vec[i];
@@ -200,7 +203,7 @@ int build_from_triplets(dpgo_problem *p, std::vector<BlockTriplet> &trip, unsign
   // upload
   cudaSetDevice(p->device);
   free_dev(p->d_rowptr); free_dev(p->d_bcol); free_dev(p->d_bval); free_dev(p->d_dinv); free_dev(p->d_pinv);
-  free_dev(p->d_cta_rows); free_dev(p->d_partials);
+  free_dev(p->d_cta_rows); free_dev(p->d_partials); free_dev(p->d_dense_part);
   p->have_Q = false;
   DPGO_CUDA(cudaMalloc(&p->d_rowptr, sizeof(int) * (n + 1)));
   DPGO_CUDA(cudaMalloc(&p->d_bcol, sizeof(int) * std::max<int64_t>(nb, 1)));
@@ -227,6 +230,10 @@ int build_from_triplets(dpgo_problem *p, std::vector<BlockTriplet> &trip, unsign
     const size_t N = (size_t)p->N;
     if (N * N * sizeof(double) > (size_t)48 << 30)
       return fail(DPGO_ERR_UNSUPPORTED, "dense exact preconditioner limited to N^2*8 <= 48 GiB; use block-Jacobi");
+    p->dense_per = (int)((N + grid - 1) / grid);
+    if (p->dense_per > dpgo::DENSE_PER_MAX)
+      return fail(DPGO_ERR_UNSUPPORTED, "dense exact preconditioner: N too large for the per-CTA slab; use block-Jacobi");
+    DPGO_CUDA(cudaMalloc(&p->d_dense_part, sizeof(double) * (size_t)grid * p->r * N));
     DPGO_CUDA(cudaMalloc(&p->d_pinv, N * N * sizeof(double)));
     DPGO_CUDA(cudaMemsetAsync(p->d_pinv, 0, N * N * sizeof(double), p->stream));
     // scatter Q + 0.1 I into the dense buffer on the host side of a staging copy would cost N^2 of
@@ -389,7 +396,7 @@ int dpgo_problem_destroy(dpgo_problem_t *p) {
   cudaSetDevice(p->device);
   if (p->stream) cudaStreamSynchronize(p->stream);
   free_dev(p->d_rowptr); free_dev(p->d_bcol); free_dev(p->d_cta_rows); free_dev(p->d_bval);
-  free_dev(p->d_dinv); free_dev(p->d_pinv); free_dev(p->d_G);
+  free_dev(p->d_dinv); free_dev(p->d_pinv); free_dev(p->d_dense_part); free_dev(p->d_G);
   for (int i = 0; i < dpgo::V_COUNT; ++i) free_dev(p->d_vec[i]);
   free_dev(p->d_S[0]); free_dev(p->d_S[1]); free_dev(p->d_partials); free_dev(p->d_bar); free_dev(p->d_result);
   free_dev(p->d_public); free_dev(p->d_pose_ids); free_dev(p->d_pose_ptr); free_dev(p->d_edge_slot);

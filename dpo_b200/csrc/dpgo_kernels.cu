@@ -237,70 +237,51 @@ __device__ void phase_update(const KParams &kp, int cb, const double *dcur, doub
 // ---------------------------------------------------------------------------------------------
 // Dense-inverse preconditioner (parity mode; ref: QuadraticProblem::PreConditioner,
 // src/QuadraticProblem.cpp:75-87 = CHOLMOD solve with Q+0.1I, then projection):
-//   phase_dense : T = V * Pinv      (Pinv symmetric N x N, streamed once, coalesced columns)
-//   phase_pz    : Z = P_X(T), acc[0] = <Z, V>
+//   phase_dense : CTA b owns the row slab [k0,k1) of the symmetric Pinv (a contiguous 8*N*(k1-k0) byte
+//                 stream, every load coalesced, up to `per` independent loads in flight per thread) and
+//                 writes its partial product  part_b = V[:, k0:k1] * Pinv[k0:k1, :]   (r x N)
+//   phase_pz    : T = sum_b part_b in fixed CTA order (deterministic), Z = P_X(T), acc[0] = <Z, V>
 // ---------------------------------------------------------------------------------------------
-template <int R, int CT>
-__device__ void dense_cols(const KParams &kp, const double *V, double *T, double *sV, int KC, int c0, int c1) {
+template <int R> __device__ void phase_dense(const KParams &kp, const double *V, double *sV) {
   const int N = kp.N;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
-  const int ngroups = (c1 - c0 + CT - 1) / CT;
-  const int rounds = (ngroups + nwarps - 1) / nwarps;
-  for (int rd = 0; rd < rounds; ++rd) {
-    const int grp = rd * nwarps + warp;
-    const int col = c0 + grp * CT;
-    const bool wact = grp < ngroups;
-    double acc[CT][R];
+  const int per = kp.dense_per;
+  const int k0 = min(N, (int)blockIdx.x * per), k1 = min(N, k0 + per);
+  const int nk = k1 - k0;
+  if (nk <= 0) return;
+  for (int q = threadIdx.x; q < nk * R; q += blockDim.x) sV[q] = __ldcg(V + (size_t)k0 * R + q);
+  __syncthreads();
+  double *part = kp.dense_part + (size_t)blockIdx.x * R * N;
+  const double *P = kp.pinv + (size_t)k0 * N;
+  for (int c = threadIdx.x; c < N; c += blockDim.x) {
+    double acc[R];
 #pragma unroll
-    for (int t = 0; t < CT; ++t)
+    for (int a = 0; a < R; ++a) acc[a] = 0.0;
+    int kk = 0;
+    for (; kk + 8 <= nk; kk += 8) {
+      double p[8];
 #pragma unroll
-      for (int a = 0; a < R; ++a) acc[t][a] = 0.0;
-    for (int k0 = 0; k0 < N; k0 += KC) {
-      const int kn = min(KC, N - k0);
-      __syncthreads();
-      for (int q = threadIdx.x; q < kn * R; q += blockDim.x) sV[q] = __ldcg(V + (size_t)k0 * R + q);
-      __syncthreads();
-      if (wact) {
-        for (int kk = lane; kk < kn; kk += 32) {
-          double p[CT];
+      for (int u = 0; u < 8; ++u) p[u] = ld_const(P + (size_t)(kk + u) * N + c);
 #pragma unroll
-          for (int t = 0; t < CT; ++t)
-            p[t] = (col + t < c1) ? ld_const(kp.pinv + (size_t)(col + t) * N + k0 + kk) : 0.0;
+      for (int u = 0; u < 8; ++u)
 #pragma unroll
-          for (int a = 0; a < R; ++a) {
-            const double v = sV[kk * R + a];
-#pragma unroll
-            for (int t = 0; t < CT; ++t) acc[t][a] = fma(v, p[t], acc[t][a]);
-          }
-        }
-      }
+        for (int a = 0; a < R; ++a) acc[a] = fma(sV[(kk + u) * R + a], p[u], acc[a]);
     }
-    if (wact) {
+    for (; kk < nk; ++kk) {
+      const double p = ld_const(P + (size_t)kk * N + c);
 #pragma unroll
-      for (int t = 0; t < CT; ++t)
-#pragma unroll
-        for (int a = 0; a < R; ++a) {
-          const double s = warp_sum(acc[t][a]);
-          if (lane == 0 && col + t < c1) T[(size_t)(col + t) * R + a] = s;
-        }
+      for (int a = 0; a < R; ++a) acc[a] = fma(sV[kk * R + a], p, acc[a]);
     }
+#pragma unroll
+    for (int a = 0; a < R; ++a) part[(size_t)c * R + a] = acc[a];
   }
 }
 
-template <int R> __device__ void phase_dense(const KParams &kp, const double *V, double *T, double *sV, int KC) {
-  const int N = kp.N;
-  const int per = (N + kp.grid - 1) / kp.grid;
-  const int c0 = min(N, (int)blockIdx.x * per), c1 = min(N, c0 + per);
-  const int nwarps = blockDim.x >> 5;
-  if (c1 - c0 >= 4 * nwarps) dense_cols<R, 4>(kp, V, T, sV, KC, c0, c1);
-  else dense_cols<R, 1>(kp, V, T, sV, KC, c0, c1);
-}
-
 template <int R, int DH>
-__device__ void phase_pz(const KParams &kp, int cb, const double *V, const double *T, double *Zout,
-                         double (&acc)[NRED]) {
+__device__ void phase_pz(const KParams &kp, int cb, const double *V, double *Zout, double (&acc)[NRED]) {
   constexpr int TS = R * DH;
   const double *X = kp.v[V_X0 + cb];
+  const int nslabs = (kp.N + kp.dense_per - 1) / kp.dense_per;
+  const size_t stride = (size_t)R * kp.N;
   RowIter<R> it(kp);
   const bool valid = (it.a < R) && (it.c < DH);
   const int e = it.c * R + it.a;
@@ -311,7 +292,17 @@ __device__ void phase_pz(const KParams &kp, int cb, const double *V, const doubl
     const bool ld = act && valid;
     const size_t idx = (size_t)js * TS + e;
     const double x = ld ? __ldcg(X + idx) : 0.0;
-    const double t = ld ? __ldcg(T + idx) : 0.0;
+    double t = 0.0;
+    if (ld) {
+      const double *pp = kp.dense_part + idx;
+      int b = 0;
+      for (; b + 4 <= nslabs; b += 4) {
+        const double t0 = __ldcg(pp + (size_t)b * stride), t1 = __ldcg(pp + (size_t)(b + 1) * stride);
+        const double t2 = __ldcg(pp + (size_t)(b + 2) * stride), t3 = __ldcg(pp + (size_t)(b + 3) * stride);
+        t += t0; t += t1; t += t2; t += t3;
+      }
+      for (; b < nslabs; ++b) t += __ldcg(pp + (size_t)b * stride);
+    }
     double ya[3], sym[3];
     const double z = tangent_project_elem<R, DH>(x, t, it.a, it.c, ya, sym);
     if (ld) {
@@ -402,8 +393,7 @@ template <int R, int DH> __global__ void __launch_bounds__(OPT_THREADS, 1) k_opt
   BlockCtx bc;
   bc.sm_warp = smem;
   bc.sm_out = smem + (OPT_THREADS / 32) * NRED;
-  double *sV = bc.sm_out + NRED;                // dense-preconditioner staging (KC * R doubles)
-  const int KC = 1024;
+  double *sV = bc.sm_out + NRED;                // dense-preconditioner staging (dense_per * R doubles)
   bc.epoch = *kp.bar_epoch;
   bc.parity = 0;
   const dpgo_opt_params_t prm = kp.prm;
@@ -420,9 +410,9 @@ template <int R, int DH> __global__ void __launch_bounds__(OPT_THREADS, 1) k_opt
   // ---- single-operation entry points -------------------------------------------------------
   if (kp.op == OP_PRECON) {
     if (precond == DPGO_PRECOND_DENSE_EXACT) {
-      phase_dense<R>(kp, kp.v[V_AUX], kp.v[V_T], sV, KC);
+      phase_dense<R>(kp, kp.v[V_AUX], sV);
       zero(acc); phase_end(kp, bc, acc);
-      zero(acc); phase_pz<R, DH>(kp, 0, kp.v[V_AUX], kp.v[V_T], kp.v[V_Z], acc);
+      zero(acc); phase_pz<R, DH>(kp, 0, kp.v[V_AUX], kp.v[V_Z], acc);
       phase_end(kp, bc, acc);
     } else {
       // reuse phase_update with res := AUX (first = false, alpha = 0 would need RES); do it directly
@@ -509,9 +499,9 @@ template <int R, int DH> __global__ void __launch_bounds__(OPT_THREADS, 1) k_opt
     while (true) {
       // -- z0 = M^-1 g for the dense preconditioner (pose-local ones were fused into phase E)
       if (!z0_valid) {
-        phase_dense<R>(kp, kp.v[V_RG0 + cb], kp.v[V_T], sV, KC);
+        phase_dense<R>(kp, kp.v[V_RG0 + cb], sV);
         zero(acc); phase_end(kp, bc, acc);
-        zero(acc); phase_pz<R, DH>(kp, cb, kp.v[V_RG0 + cb], kp.v[V_T], kp.v[V_Z00 + cb], acc);
+        zero(acc); phase_pz<R, DH>(kp, cb, kp.v[V_RG0 + cb], kp.v[V_Z00 + cb], acc);
         phase_end(kp, bc, acc);
         zr0 = acc[0];
         z0_valid = true;
@@ -556,9 +546,9 @@ template <int R, int DH> __global__ void __launch_bounds__(OPT_THREADS, 1) k_opt
         }
         double zr_new = acc[1];
         if (precond == DPGO_PRECOND_DENSE_EXACT) {
-          phase_dense<R>(kp, kp.v[V_RES], kp.v[V_T], sV, KC);
+          phase_dense<R>(kp, kp.v[V_RES], sV);
           zero(acc); phase_end(kp, bc, acc);
-          zero(acc); phase_pz<R, DH>(kp, cb, kp.v[V_RES], kp.v[V_T], kp.v[V_Z], acc);
+          zero(acc); phase_pz<R, DH>(kp, cb, kp.v[V_RES], kp.v[V_Z], acc);
           phase_end(kp, bc, acc);
           zr_new = acc[0];
         }
@@ -772,7 +762,7 @@ __global__ void k_build_G(int nposes, const int *__restrict__ pose_ids, const in
 // launchers
 // ---------------------------------------------------------------------------------------------
 template <int R, int DH> static cudaError_t launch_optimize_t(const KParams &kp, cudaStream_t stream) {
-  const size_t smem = ((OPT_THREADS / 32) * NRED + NRED + 1024 * R) * sizeof(double);
+  const size_t smem = ((OPT_THREADS / 32) * NRED + NRED + (size_t)DENSE_PER_MAX * R) * sizeof(double);
   static bool attr_set[64] = {};
   int dev = 0;
   cudaGetDevice(&dev);
@@ -786,7 +776,7 @@ template <int R, int DH> static cudaError_t launch_optimize_t(const KParams &kp,
 }
 
 template <int R, int DH> static int max_grid_t(int device) {
-  const size_t smem = ((OPT_THREADS / 32) * NRED + NRED + 1024 * R) * sizeof(double);
+  const size_t smem = ((OPT_THREADS / 32) * NRED + NRED + (size_t)DENSE_PER_MAX * R) * sizeof(double);
   cudaFuncSetAttribute(k_optimize<R, DH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   int per_sm = 0, sms = 0;
   if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_optimize<R, DH>, OPT_THREADS, smem) != cudaSuccess) return 0;

@@ -30,6 +30,7 @@ enum OpCode {
 
 constexpr int NRED = 4;            // scalars reduced per phase
 constexpr int OPT_THREADS = 512;   // persistent kernel block size
+constexpr int DENSE_PER_MAX = 1024; // max rows of the dense inverse one CTA owns (smem staging of V)
 
 struct KParams {
   int n;                 // poses
@@ -41,6 +42,8 @@ struct KParams {
   const double *bval;    // nb*16
   const double *dinv;    // n*16   block-Jacobi inverse blocks, may be null
   const double *pinv;    // N*N    dense inverse of Q+0.1I, may be null
+  double *dense_part;    // grid * r * N  per-CTA partial products of the dense preconditioner
+  int dense_per;         // rows of pinv per CTA
   const int *cta_rows;   // grid+1 balanced row partition
   const double *G;       // linear term r x N
   double *v[V_COUNT];

@@ -182,7 +182,15 @@ class QuadraticProblem:
 
     # -- device-resident path ----------------------------------------------------------------------------
     def set_stream(self, cuda_stream: Optional[int]) -> None:
-        capi.check(self._lib.dpgo_problem_set_stream(self._h, C.c_void_p(cuda_stream) if cuda_stream else None))
+        """cuda_stream: a cudaStream_t handle; 0 means the legacy default stream (torch's default), None
+        restores the handle's own non-blocking stream."""
+        if cuda_stream is None:
+            arg = None
+        elif cuda_stream == 0:
+            arg = C.c_void_p(1)                      # cudaStreamLegacy
+        else:
+            arg = C.c_void_p(cuda_stream)
+        capi.check(self._lib.dpgo_problem_set_stream(self._h, arg))
 
     def sync(self) -> None:
         capi.check(self._lib.dpgo_problem_sync(self._h))
