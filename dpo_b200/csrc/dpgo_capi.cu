@@ -6,6 +6,7 @@
 #include <chrono>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <numeric>
 #include <string>
@@ -50,6 +51,8 @@ struct dpgo_problem {
   bool have_Q = false;
   unsigned precond_mask = 0;
   int *d_rowptr = nullptr, *d_bcol = nullptr, *d_cta_rows = nullptr;
+  int2 *d_groups = nullptr;      // row groups of the TMA-fed SpMV
+  int ngroups = 0;
   double *d_bval = nullptr, *d_dinv = nullptr, *d_pinv = nullptr, *d_dense_part = nullptr;
   int dense_per = 1;
   // vectors
@@ -96,6 +99,14 @@ void fill_kparams(const dpgo_problem *p, dpgo::KParams &kp, int op, const dpgo_o
   kp.bar_epoch = p->d_bar + 1;
   kp.prm = prm;
   kp.result = p->d_result;
+}
+
+cudaError_t run_spmv(const dpgo_problem *p, const double *X, const double *G, double *out) {
+  static const bool force_gather = [] { const char *e = std::getenv("DPGO_SPMV_KERNEL"); return e && std::string(e) == "gather"; }();
+  if (p->ngroups > 0 && !force_gather)
+    return dpgo::launch_spmv_tma(p->r, p->dh, p->ngroups, p->d_groups, p->d_rowptr, p->d_bcol, p->d_bval, X, G, out, p->sms,
+                                 p->stream);
+  return dpgo::launch_spmv(p->r, p->dh, p->n, p->d_rowptr, p->d_bcol, p->d_bval, X, G, out, p->stream);
 }
 
 int check_precond(const dpgo_problem *p, int precond) {
@@ -203,10 +214,14 @@ int build_from_triplets(dpgo_problem *p, std::vector<BlockTriplet> &trip, unsign
   // upload
   cudaSetDevice(p->device);
   free_dev(p->d_rowptr); free_dev(p->d_bcol); free_dev(p->d_bval); free_dev(p->d_dinv); free_dev(p->d_pinv);
-  free_dev(p->d_cta_rows); free_dev(p->d_partials); free_dev(p->d_dense_part);
+  free_dev(p->d_cta_rows); free_dev(p->d_partials); free_dev(p->d_dense_part); free_dev(p->d_groups);
   p->have_Q = false;
-  DPGO_CUDA(cudaMalloc(&p->d_rowptr, sizeof(int) * (n + 1)));
-  DPGO_CUDA(cudaMalloc(&p->d_bcol, sizeof(int) * std::max<int64_t>(nb, 1)));
+  p->ngroups = 0;
+  // +8 ints of slack: the bulk-TMA windows are rounded out to 16 bytes
+  DPGO_CUDA(cudaMalloc(&p->d_rowptr, sizeof(int) * (n + 1 + 8)));
+  DPGO_CUDA(cudaMalloc(&p->d_bcol, sizeof(int) * (std::max<int64_t>(nb, 1) + 8)));
+  DPGO_CUDA(cudaMemsetAsync(p->d_rowptr, 0, sizeof(int) * (n + 1 + 8), p->stream));
+  DPGO_CUDA(cudaMemsetAsync(p->d_bcol, 0, sizeof(int) * (std::max<int64_t>(nb, 1) + 8), p->stream));
   DPGO_CUDA(cudaMalloc(&p->d_bval, sizeof(double) * 16 * std::max<int64_t>(nb, 1)));
   DPGO_CUDA(cudaMalloc(&p->d_cta_rows, sizeof(int) * (grid + 1)));
   DPGO_CUDA(cudaMalloc(&p->d_partials, sizeof(double) * 2 * grid * dpgo::NRED));
@@ -220,6 +235,29 @@ int build_from_triplets(dpgo_problem *p, std::vector<BlockTriplet> &trip, unsign
   if (!dinv.empty()) {
     DPGO_CUDA(cudaMalloc(&p->d_dinv, sizeof(double) * dinv.size()));
     DPGO_CUDA(cudaMemcpyAsync(p->d_dinv, dinv.data(), sizeof(double) * dinv.size(), cudaMemcpyHostToDevice, p->stream));
+  }
+  // row groups for the TMA-fed SpMV: consecutive rows, <= SPMV_GROUP_BLOCKS blocks and rows each
+  {
+    const int BT = dpgo::SPMV_GROUP_BLOCKS;
+    std::vector<int2> groups;
+    bool ok = true;
+    int rr = 0;
+    while (rr < n) {
+      const int start = rr;
+      int blocks = 0;
+      while (rr < n && (rr - start) < BT && blocks + (rowptr[rr + 1] - rowptr[rr]) <= BT) {
+        blocks += rowptr[rr + 1] - rowptr[rr];
+        ++rr;
+      }
+      if (rr == start) { ok = false; break; }        // a single row exceeds the stage: fall back to the gather kernel
+      groups.push_back(make_int2(start, rowptr[start]));
+    }
+    if (ok && nb > 0) {
+      groups.push_back(make_int2(n, (int)nb));
+      DPGO_CUDA(cudaMalloc(&p->d_groups, sizeof(int2) * groups.size()));
+      DPGO_CUDA(cudaMemcpyAsync(p->d_groups, groups.data(), sizeof(int2) * groups.size(), cudaMemcpyHostToDevice, p->stream));
+      p->ngroups = (int)groups.size() - 1;
+    }
   }
   DPGO_CUDA(cudaStreamSynchronize(p->stream));
   p->nb = nb;
@@ -395,7 +433,7 @@ int dpgo_problem_destroy(dpgo_problem_t *p) {
   if (!p) return DPGO_OK;
   cudaSetDevice(p->device);
   if (p->stream) cudaStreamSynchronize(p->stream);
-  free_dev(p->d_rowptr); free_dev(p->d_bcol); free_dev(p->d_cta_rows); free_dev(p->d_bval);
+  free_dev(p->d_rowptr); free_dev(p->d_bcol); free_dev(p->d_cta_rows); free_dev(p->d_bval); free_dev(p->d_groups);
   free_dev(p->d_dinv); free_dev(p->d_pinv); free_dev(p->d_dense_part); free_dev(p->d_G);
   for (int i = 0; i < dpgo::V_COUNT; ++i) free_dev(p->d_vec[i]);
   free_dev(p->d_S[0]); free_dev(p->d_S[1]); free_dev(p->d_partials); free_dev(p->d_bar); free_dev(p->d_result);
@@ -537,8 +575,7 @@ int dpgo_problem_ehess(dpgo_problem_t *p, const double *V_host, double *out_host
   DPGO_REQUIRE(V_host && out_host, DPGO_ERR_INVALID_ARG, "null argument");
   DPGO_REQUIRE(p->have_Q, DPGO_ERR_STATE, "set_Q has not been called");
   DPGO_TRY(upload_vec(p, dpgo::V_AUX, V_host));
-  DPGO_CUDA(dpgo::launch_spmv(p->r, p->dh, p->n, p->d_rowptr, p->d_bcol, p->d_bval, p->d_vec[dpgo::V_AUX], nullptr,
-                              p->d_vec[dpgo::V_HD], p->stream));
+  DPGO_CUDA(run_spmv(p, p->d_vec[dpgo::V_AUX], nullptr, p->d_vec[dpgo::V_HD]));
   DPGO_TRY(download_vec(p, dpgo::V_HD, out_host));
   DPGO_CUDA(cudaStreamSynchronize(p->stream));
   return DPGO_OK;
@@ -705,8 +742,7 @@ int dpgo_spmv_device(dpgo_problem_t *p, const double *X_dev, double *out_dev, in
   DPGO_CHECK_HANDLE(p);
   DPGO_REQUIRE(X_dev && out_dev, DPGO_ERR_INVALID_ARG, "null argument");
   DPGO_REQUIRE(p->have_Q, DPGO_ERR_STATE, "set_Q has not been called");
-  DPGO_CUDA(dpgo::launch_spmv(p->r, p->dh, p->n, p->d_rowptr, p->d_bcol, p->d_bval, X_dev, add_G ? p->d_G : nullptr,
-                              out_dev, p->stream));
+  DPGO_CUDA(run_spmv(p, X_dev, add_G ? p->d_G : nullptr, out_dev));
   return DPGO_OK;
 }
 

@@ -1,5 +1,6 @@
 // dpgo_kernels.cuh -- kernel-side parameter block shared by dpgo_kernels.cu and dpgo_capi.cu
 #pragma once
+#include <cuda_runtime.h>
 #include <stdint.h>
 #include "../../include/dpgo_b200.h"
 
@@ -30,6 +31,7 @@ enum OpCode {
 
 constexpr int NRED = 4;            // scalars reduced per phase
 constexpr int OPT_THREADS = 512;   // persistent kernel block size
+constexpr int SPMV_GROUP_BLOCKS = 256;  // blocks per row group of the TMA-fed SpMV (32 KB of Q per smem stage)
 constexpr int DENSE_PER_MAX = 1024; // max rows of the dense inverse one CTA owns (smem staging of V)
 
 struct KParams {
@@ -59,6 +61,9 @@ struct KParams {
 cudaError_t launch_optimize(int r, int dh, const KParams &kp, cudaStream_t stream);
 cudaError_t launch_spmv(int r, int dh, int n, const int *rowptr, const int *bcol, const double *bval,
                         const double *X, const double *G, double *out, cudaStream_t stream);
+cudaError_t launch_spmv_tma(int r, int dh, int ngroups, const int2 *groups, const int *rowptr, const int *bcol,
+                            const double *bval, const double *X, const double *G, double *out, int sms,
+                            cudaStream_t stream);
 int optimize_max_grid(int r, int dh, int device);   // co-resident CTA count for the persistent kernel
 cudaError_t launch_stiefel_project(int r, int dh, int n, const double *M, double *out, cudaStream_t stream);
 cudaError_t launch_pack_tiles(int ts, int count, const int *pose, const double *X, double *out, cudaStream_t stream);

@@ -1,0 +1,219 @@
+// dpgo_spmv_tma.cu -- the Q.X product (Out = X Q [+ G]) as a persistent, TMA-fed streaming kernel.
+//
+// Why: the measurement-block stream (128 B per block, contiguous for a contiguous range of pose tiles)
+// is >75 % of the algorithmic bytes; a per-row gather kernel serialises 5-8 dependent DRAM latencies per
+// row (rowptr -> indices -> blocks, batch after batch) and tops out near 28 % of HBM peak (profiles/).
+// Here the row structure and the DRAM stream are decoupled:
+//   * the host cuts the pose tiles into "row groups" of <= BT blocks (consecutive rows);
+//   * each CTA walks its groups with an NSTAGE-deep ring of shared-memory stages; one elected thread
+//     issues three 1-D bulk TMA copies per group (cp.async.bulk ... mbarrier::complete_tx): the 4x4 blocks,
+//     their column indices, and the row-pointer slice -- 100+ KB in flight per SM, L2 evict-first policy
+//     so the stream does not push the pose tiles (X) out of L2;
+//   * the warps consume a group from shared memory: indices and blocks come from smem (no dependent global
+//     round trips), only the X gathers go to L2, issued for a whole batch of 8 blocks at once.
+// Lane mapping and reduce-scatter are those of dpgo_device.cuh (lane (a,k) holds P_i[a,k] and row k of
+// the block; result element (a,c) ends in lane (a,c)).
+#include "dpgo_device.cuh"
+#include "dpgo_kernels.cuh"
+
+namespace dpgo {
+
+namespace {
+
+constexpr int TMA_THREADS = 512;
+constexpr int TMA_NSTAGE = 3;
+constexpr int SPMV_BATCH = 12;   // blocks whose loads are issued together (predicated); rows <= 12 blocks take one round
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, unsigned parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_LOOP:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE;\n"
+      "bra WAIT_LOOP;\n"
+      "DONE:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ uint64_t policy_evict_first() {
+  uint64_t pol;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+// 1-D bulk copy global -> shared, completion reported on an mbarrier (SASS: UBLKCP)
+__device__ __forceinline__ void tma_load_1d(void *dst_smem, const void *src_gmem, unsigned bytes, uint64_t *bar, uint64_t pol) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(
+          smem_u32(dst_smem)),
+      "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)), "l"(pol)
+      : "memory");
+}
+
+}  // namespace
+
+// group g covers rows [gi[g].x, gi[g+1].x) and blocks [gi[g].y, gi[g+1].y)
+template <int R, int DH, int BT>
+__global__ void __launch_bounds__(TMA_THREADS, 2)
+    k_spmv_tma(int ngroups, const int2 *__restrict__ gi, const int *__restrict__ rowptr, const int *__restrict__ bcol,
+               const double *__restrict__ bval, const double *__restrict__ X, const double *__restrict__ G,
+               double *__restrict__ out) {
+  constexpr int TS = R * DH;
+  constexpr int IDX_CAP = BT + 8;        // ints per stage for indices (alignment slack)
+  constexpr int RP_CAP = BT + 12;        // ints per stage for the row-pointer slice (a group has <= BT rows... see host)
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  double *sq = reinterpret_cast<double *>(smem_raw);                                     // NSTAGE * BT * 16
+  int *sidx = reinterpret_cast<int *>(smem_raw + (size_t)TMA_NSTAGE * BT * 128);        // NSTAGE * IDX_CAP
+  int *srp = sidx + TMA_NSTAGE * IDX_CAP;                                                // NSTAGE * RP_CAP
+  uint64_t *bars = reinterpret_cast<uint64_t *>(srp + TMA_NSTAGE * RP_CAP);              // NSTAGE
+
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  constexpr int NWARPS = TMA_THREADS / 32;
+  const int a = lane >> 2, k = lane & 3;
+  const bool valid = (a < R) && (k < DH);
+  const int off = k * R + a;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < TMA_NSTAGE; ++s) mbar_init(&bars[s], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  const uint64_t pol = policy_evict_first();
+
+  auto issue = [&](int g, int s) {
+    const int2 g0 = __ldg(gi + g), g1 = __ldg(gi + g + 1);
+    const int b0 = g0.y, b1 = g1.y, r0 = g0.x, r1 = g1.x;
+    const unsigned qbytes = (unsigned)(b1 - b0) * 128u;
+    const int ib = b0 & ~3;                                   // 16-byte aligned index window
+    const unsigned ibytes = (unsigned)(((b1 - ib) + 3) & ~3) * 4u;
+    const int rb = r0 & ~3;                                   // rowptr[r0 .. r1] inclusive
+    const unsigned rbytes = (unsigned)(((r1 + 1 - rb) + 3) & ~3) * 4u;
+    mbar_expect_tx(&bars[s], qbytes + ibytes + rbytes);
+    if (qbytes) tma_load_1d(sq + (size_t)s * BT * 16, bval + (size_t)b0 * 16, qbytes, &bars[s], pol);
+    tma_load_1d(sidx + s * IDX_CAP, bcol + ib, ibytes, &bars[s], pol);
+    tma_load_1d(srp + s * RP_CAP, rowptr + rb, rbytes, &bars[s], pol);
+  };
+
+  // prologue: fill the ring
+  int issued = 0;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < TMA_NSTAGE; ++s) {
+      const int g = blockIdx.x + s * gridDim.x;
+      if (g < ngroups) issue(g, s);
+    }
+  }
+  (void)issued;
+
+  int it = 0;
+  for (int g = blockIdx.x; g < ngroups; g += gridDim.x, ++it) {
+    const int s = it % TMA_NSTAGE;
+    const unsigned parity = (unsigned)((it / TMA_NSTAGE) & 1);
+    mbar_wait(&bars[s], parity);
+    const int2 g0 = __ldg(gi + g), g1 = __ldg(gi + g + 1);
+    const int r0 = g0.x, r1 = g1.x, b0 = g0.y;
+    const double *q_s = sq + (size_t)s * BT * 16;
+    const int *idx_s = sidx + s * IDX_CAP + (b0 - (b0 & ~3));
+    const int *rp_s = srp + s * RP_CAP + (r0 - (r0 & ~3));
+
+    // One warp per pose tile.  The 4x4 block product runs on the fp64 tensor pipe (mma.sync m8n8k4, SASS DMMA):
+    // the A fragment IS the lane mapping (lane = 4a + k holds P_i[a,k]), the B fragment is one 8-byte shared
+    // load per lane (lanes 0..15 cover the 128-byte block exactly once -> a single smem wavefront), and the
+    // accumulator fragment leaves Out_j[a, 2k..2k+1] in lane (a,k), k < 2 -- no shuffles, no 128-bit smem
+    // broadcasts.  This cuts the L1/smem wavefronts per block from ~13 to ~4 (the measured limiter, profiles/).
+    for (int j = r0 + warp; j < r1; j += NWARPS) {
+      const int lb0 = rp_s[j - r0] - b0, lb1 = rp_s[j - r0 + 1] - b0;
+      double c0 = 0.0, c1 = 0.0, e0 = 0.0, e1 = 0.0;      // two accumulator pairs (shorter DMMA chains)
+      const int bn = lane >> 2;                            // B fragment: column n = lane>>2, row k = lane&3
+      const bool bvalid = bn < 4;
+      const int boff = k * 4 + bn;
+      for (int b = lb0; b < lb1; b += SPMV_BATCH) {
+        double x[SPMV_BATCH];
+#pragma unroll
+        for (int u = 0; u < SPMV_BATCH; ++u) {             // all global gathers of the batch in flight together
+          const bool in = (b + u < lb1);
+          const int i = in ? idx_s[b + u] : 0;
+          x[u] = (in && valid) ? __ldg(X + (size_t)i * TS + off) : 0.0;
+        }
+#pragma unroll
+        for (int u = 0; u < SPMV_BATCH; u += 2) {
+          const double q0 = (b + u < lb1 && bvalid) ? q_s[(size_t)(b + u) * 16 + boff] : 0.0;
+          const double q1 = (b + u + 1 < lb1 && bvalid) ? q_s[(size_t)(b + u + 1) * 16 + boff] : 0.0;
+          asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                       : "+d"(c0), "+d"(c1) : "d"(x[u]), "d"(q0));
+          asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                       : "+d"(e0), "+d"(e1) : "d"(x[u + 1]), "d"(q1));
+        }
+      }
+      c0 += e0;
+      c1 += e1;
+      // lane (a, k): c0 = Out_j[a, 2k], c1 = Out_j[a, 2k+1]
+      if (a < R && k < 2) {
+        const int cA = 2 * k, cB = 2 * k + 1;
+        const size_t base = (size_t)j * TS + a;
+        if (cA < DH) {
+          double v = c0;
+          if (G != nullptr) v += __ldg(G + base + (size_t)cA * R);
+          out[base + (size_t)cA * R] = v;
+        }
+        if (cB < DH) {
+          double v = c1;
+          if (G != nullptr) v += __ldg(G + base + (size_t)cB * R);
+          out[base + (size_t)cB * R] = v;
+        }
+      }
+    }
+    __syncthreads();                                        // every warp is done with stage s
+    if (threadIdx.x == 0) {
+      const int gn = g + TMA_NSTAGE * gridDim.x;
+      if (gn < ngroups) issue(gn, s);
+    }
+  }
+}
+
+template <int R, int DH> static cudaError_t launch_tma_t(int ngroups, const int2 *gi, const int *rowptr, const int *bcol,
+                                                         const double *bval, const double *X, const double *G, double *out,
+                                                         int sms, cudaStream_t stream) {
+  constexpr int BT = SPMV_GROUP_BLOCKS;
+  const size_t smem = (size_t)TMA_NSTAGE * BT * 128 + (size_t)TMA_NSTAGE * (BT + 8) * 4 + (size_t)TMA_NSTAGE * (BT + 12) * 4 +
+                      TMA_NSTAGE * 8 + 128;
+  static bool attr_set[64] = {};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 64 || !attr_set[dev]) {
+    cudaError_t e = cudaFuncSetAttribute(k_spmv_tma<R, DH, BT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    if (dev >= 0 && dev < 64) attr_set[dev] = true;
+  }
+  int grid = 2 * sms;
+  if (grid > ngroups) grid = ngroups;
+  if (grid < 1) grid = 1;
+  k_spmv_tma<R, DH, BT><<<grid, TMA_THREADS, smem, stream>>>(ngroups, gi, rowptr, bcol, bval, X, G, out);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_spmv_tma(int r, int dh, int ngroups, const int2 *gi, const int *rowptr, const int *bcol,
+                            const double *bval, const double *X, const double *G, double *out, int sms,
+                            cudaStream_t stream) {
+  cudaError_t e = cudaErrorInvalidValue;
+  if (dh == 4) {
+    if (r == 3) e = launch_tma_t<3, 4>(ngroups, gi, rowptr, bcol, bval, X, G, out, sms, stream);
+    else if (r == 4) e = launch_tma_t<4, 4>(ngroups, gi, rowptr, bcol, bval, X, G, out, sms, stream);
+    else if (r == 5) e = launch_tma_t<5, 4>(ngroups, gi, rowptr, bcol, bval, X, G, out, sms, stream);
+  } else if (dh == 3) {
+    if (r == 2) e = launch_tma_t<2, 3>(ngroups, gi, rowptr, bcol, bval, X, G, out, sms, stream);
+    else if (r == 3) e = launch_tma_t<3, 3>(ngroups, gi, rowptr, bcol, bval, X, G, out, sms, stream);
+    else if (r == 5) e = launch_tma_t<5, 3>(ngroups, gi, rowptr, bcol, bval, X, G, out, sms, stream);
+  }
+  return e;
+}
+
+}  // namespace dpgo

@@ -98,3 +98,42 @@ def test_argument_errors(data_dir):
     X = orc.manifold_project(np.random.default_rng(0).standard_normal((3, 16)), 3)
     assert p.f(X) == 0.0
     assert np.abs(p.EucGrad(X)).max() == 0.0
+
+
+@pytest.mark.parametrize("dims,r", [((12, 10, 6), 5), ((30, 30, 20), 5), ((30, 30, 20), 3), ((50, 40, 30), 5)])
+def test_spmv_device_synthetic_grid(dims, r):
+    """The stand-alone Q.X kernel (TMA-fed row groups) on graphs spanning many groups, against scipy CSR.
+    Size-independent property as well: linearity  Q(aX + bY) = a QX + b QY."""
+    import torch
+    import dpo_b200 as dp
+    from dpo_b200 import posegraph as pg
+    edges, n, _ = pg.synthetic_grid_graph(*dims, edges_per_pose=4.0, seed=1)
+    Q = pg.constructConnectionLaplacianSE(edges, n)
+    prob = dp.QuadraticProblem(n, 3, r, preconditioners=(dp.PRECOND_BLOCK_JACOBI,))
+    prob.setQ_blocks(*pg.connection_laplacian_blocks(edges))
+    prob.set_stream(torch.cuda.current_stream().cuda_stream)
+    rng = np.random.default_rng(0)
+    X = rng.standard_normal((r, 4 * n))
+    Y = rng.standard_normal((r, 4 * n))
+
+    def run(M):
+        t = torch.from_numpy(np.asfortranarray(M).ravel(order="F").copy()).cuda()
+        o = torch.empty_like(t)
+        prob.spmv_device(t.data_ptr(), o.data_ptr(), False)
+        torch.cuda.synchronize()
+        return o.cpu().numpy().reshape(r, 4 * n, order="F")
+
+    ref = (Q @ X.T).T
+    got = run(X)
+    assert relerr(got, ref) <= 1e-13
+    lin = run(2.0 * X - 3.0 * Y)
+    assert relerr(lin, 2.0 * got - 3.0 * run(Y)) <= 1e-13
+    # with the linear term
+    G = rng.standard_normal((r, 4 * n))
+    prob.setG(G)
+    t = torch.from_numpy(np.asfortranarray(X).ravel(order="F").copy()).cuda()
+    o = torch.empty_like(t)
+    prob.spmv_device(t.data_ptr(), o.data_ptr(), True)
+    torch.cuda.synchronize()
+    assert relerr(o.cpu().numpy().reshape(r, 4 * n, order="F"), ref + G) <= 1e-13
+    assert prob.spmv_algorithmic_bytes(False) == 132 * prob.num_blocks() + 4 * (n + 1) + 64 * r * n
