@@ -21,7 +21,7 @@ namespace dpgo {
 namespace {
 
 constexpr int TMA_THREADS = 512;
-constexpr int TMA_NSTAGE = 3;
+constexpr int TMA_NSTAGE = 4;
 constexpr int SPMV_BATCH = 12;   // blocks whose loads are issued together (predicated); rows <= 12 blocks take one round
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -61,7 +61,17 @@ __device__ __forceinline__ void tma_load_1d(void *dst_smem, const void *src_gmem
 
 }  // namespace
 
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
 // group g covers rows [gi[g].x, gi[g+1].x) and blocks [gi[g].y, gi[g+1].y)
+//
+// Warp roles: warp NCONS is the producer (one lane issues the bulk TMA copies of a group as soon as its
+// stage has been released by all consumer warps -- "empty" mbarrier, count NCONS); warps 0..NCONS-1 are
+// consumers that wait on the stage's "full" mbarrier (transaction bytes), process their share of the
+// group's rows and release the stage.  No CTA-wide barrier in the steady state: fast warps run up to
+// NSTAGE-1 groups ahead.
 template <int R, int DH, int BT>
 __global__ void __launch_bounds__(TMA_THREADS, 2)
     k_spmv_tma(int ngroups, const int2 *__restrict__ gi, const int *__restrict__ rowptr, const int *__restrict__ bcol,
@@ -69,55 +79,57 @@ __global__ void __launch_bounds__(TMA_THREADS, 2)
                double *__restrict__ out) {
   constexpr int TS = R * DH;
   constexpr int IDX_CAP = BT + 8;        // ints per stage for indices (alignment slack)
-  constexpr int RP_CAP = BT + 12;        // ints per stage for the row-pointer slice (a group has <= BT rows... see host)
+  constexpr int RP_CAP = BT + 12;        // ints per stage for the row-pointer slice (a group has <= BT rows)
+  constexpr int NCONS = TMA_THREADS / 32 - 1;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   double *sq = reinterpret_cast<double *>(smem_raw);                                     // NSTAGE * BT * 16
   int *sidx = reinterpret_cast<int *>(smem_raw + (size_t)TMA_NSTAGE * BT * 128);        // NSTAGE * IDX_CAP
   int *srp = sidx + TMA_NSTAGE * IDX_CAP;                                                // NSTAGE * RP_CAP
-  uint64_t *bars = reinterpret_cast<uint64_t *>(srp + TMA_NSTAGE * RP_CAP);              // NSTAGE
+  uint64_t *full = reinterpret_cast<uint64_t *>(srp + TMA_NSTAGE * RP_CAP);              // NSTAGE
+  uint64_t *empty = full + TMA_NSTAGE;                                                    // NSTAGE
 
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  constexpr int NWARPS = TMA_THREADS / 32;
-  const int a = lane >> 2, k = lane & 3;
-  const bool valid = (a < R) && (k < DH);
-  const int off = k * R + a;
-
   if (threadIdx.x == 0) {
-    for (int s = 0; s < TMA_NSTAGE; ++s) mbar_init(&bars[s], 1);
+    for (int s = 0; s < TMA_NSTAGE; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], NCONS); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
-  const uint64_t pol = policy_evict_first();
 
-  auto issue = [&](int g, int s) {
-    const int2 g0 = __ldg(gi + g), g1 = __ldg(gi + g + 1);
-    const int b0 = g0.y, b1 = g1.y, r0 = g0.x, r1 = g1.x;
-    const unsigned qbytes = (unsigned)(b1 - b0) * 128u;
-    const int ib = b0 & ~3;                                   // 16-byte aligned index window
-    const unsigned ibytes = (unsigned)(((b1 - ib) + 3) & ~3) * 4u;
-    const int rb = r0 & ~3;                                   // rowptr[r0 .. r1] inclusive
-    const unsigned rbytes = (unsigned)(((r1 + 1 - rb) + 3) & ~3) * 4u;
-    mbar_expect_tx(&bars[s], qbytes + ibytes + rbytes);
-    if (qbytes) tma_load_1d(sq + (size_t)s * BT * 16, bval + (size_t)b0 * 16, qbytes, &bars[s], pol);
-    tma_load_1d(sidx + s * IDX_CAP, bcol + ib, ibytes, &bars[s], pol);
-    tma_load_1d(srp + s * RP_CAP, rowptr + rb, rbytes, &bars[s], pol);
-  };
-
-  // prologue: fill the ring
-  int issued = 0;
-  if (threadIdx.x == 0) {
-    for (int s = 0; s < TMA_NSTAGE; ++s) {
-      const int g = blockIdx.x + s * gridDim.x;
-      if (g < ngroups) issue(g, s);
+  if (warp == NCONS) {
+    // ---------------- producer ----------------
+    if (lane == 0) {
+      const uint64_t pol = policy_evict_first();
+      int it = 0;
+      for (int g = blockIdx.x; g < ngroups; g += gridDim.x, ++it) {
+        const int s = it % TMA_NSTAGE;
+        if (it >= TMA_NSTAGE) mbar_wait(&empty[s], (unsigned)(((it / TMA_NSTAGE) - 1) & 1));
+        const int2 g0 = __ldg(gi + g), g1 = __ldg(gi + g + 1);
+        const int b0 = g0.y, b1 = g1.y, r0 = g0.x, r1 = g1.x;
+        const unsigned qbytes = (unsigned)(b1 - b0) * 128u;
+        const int ib = b0 & ~3;                                   // 16-byte aligned index window
+        const unsigned ibytes = (unsigned)(((b1 - ib) + 3) & ~3) * 4u;
+        const int rb = r0 & ~3;                                   // rowptr[r0 .. r1] inclusive
+        const unsigned rbytes = (unsigned)(((r1 + 1 - rb) + 3) & ~3) * 4u;
+        mbar_expect_tx(&full[s], qbytes + ibytes + rbytes);
+        if (qbytes) tma_load_1d(sq + (size_t)s * BT * 16, bval + (size_t)b0 * 16, qbytes, &full[s], pol);
+        tma_load_1d(sidx + s * IDX_CAP, bcol + ib, ibytes, &full[s], pol);
+        tma_load_1d(srp + s * RP_CAP, rowptr + rb, rbytes, &full[s], pol);
+      }
     }
+    return;
   }
-  (void)issued;
 
+  // ---------------- consumers ----------------
+  const int a = lane >> 2, k = lane & 3;
+  const bool valid = (a < R) && (k < DH);
+  const int off = k * R + a;
+  const int bn = lane >> 2;                            // B fragment: column n = lane>>2, row k = lane&3
+  const bool bvalid = bn < 4;
+  const int boff = k * 4 + bn;
   int it = 0;
   for (int g = blockIdx.x; g < ngroups; g += gridDim.x, ++it) {
     const int s = it % TMA_NSTAGE;
-    const unsigned parity = (unsigned)((it / TMA_NSTAGE) & 1);
-    mbar_wait(&bars[s], parity);
+    mbar_wait(&full[s], (unsigned)((it / TMA_NSTAGE) & 1));
     const int2 g0 = __ldg(gi + g), g1 = __ldg(gi + g + 1);
     const int r0 = g0.x, r1 = g1.x, b0 = g0.y;
     const double *q_s = sq + (size_t)s * BT * 16;
@@ -128,29 +140,35 @@ __global__ void __launch_bounds__(TMA_THREADS, 2)
     // the A fragment IS the lane mapping (lane = 4a + k holds P_i[a,k]), the B fragment is one 8-byte shared
     // load per lane (lanes 0..15 cover the 128-byte block exactly once -> a single smem wavefront), and the
     // accumulator fragment leaves Out_j[a, 2k..2k+1] in lane (a,k), k < 2 -- no shuffles, no 128-bit smem
-    // broadcasts.  This cuts the L1/smem wavefronts per block from ~13 to ~4 (the measured limiter, profiles/).
-    for (int j = r0 + warp; j < r1; j += NWARPS) {
+    // broadcasts.  The starting warp rotates with the group so that short groups load all warps evenly.
+    const int wrot = (warp + it * 7) % NCONS;
+    for (int j = r0 + wrot; j < r1; j += NCONS) {
       const int lb0 = rp_s[j - r0] - b0, lb1 = rp_s[j - r0 + 1] - b0;
       double c0 = 0.0, c1 = 0.0, e0 = 0.0, e1 = 0.0;      // two accumulator pairs (shorter DMMA chains)
-      const int bn = lane >> 2;                            // B fragment: column n = lane>>2, row k = lane&3
-      const bool bvalid = bn < 4;
-      const int boff = k * 4 + bn;
       for (int b = lb0; b < lb1; b += SPMV_BATCH) {
         double x[SPMV_BATCH];
 #pragma unroll
-        for (int u = 0; u < SPMV_BATCH; ++u) {             // all global gathers of the batch in flight together
-          const bool in = (b + u < lb1);
-          const int i = in ? idx_s[b + u] : 0;
-          x[u] = (in && valid) ? __ldg(X + (size_t)i * TS + off) : 0.0;
+        for (int u = 0; u < SPMV_BATCH; u += 2) {          // all global gathers of the batch in flight together
+          if (b + u < lb1) {                                // warp-uniform
+            const int i0 = idx_s[b + u];
+            const bool in1 = (b + u + 1 < lb1);
+            const int i1 = in1 ? idx_s[b + u + 1] : i0;
+            x[u] = valid ? __ldg(X + (size_t)i0 * TS + off) : 0.0;
+            x[u + 1] = (valid && in1) ? __ldg(X + (size_t)i1 * TS + off) : 0.0;
+          }
         }
 #pragma unroll
         for (int u = 0; u < SPMV_BATCH; u += 2) {
-          const double q0 = (b + u < lb1 && bvalid) ? q_s[(size_t)(b + u) * 16 + boff] : 0.0;
-          const double q1 = (b + u + 1 < lb1 && bvalid) ? q_s[(size_t)(b + u + 1) * 16 + boff] : 0.0;
-          asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
-                       : "+d"(c0), "+d"(c1) : "d"(x[u]), "d"(q0));
-          asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
-                       : "+d"(e0), "+d"(e1) : "d"(x[u + 1]), "d"(q1));
+          if (b + u < lb1) {
+            const double q0 = bvalid ? q_s[(size_t)(b + u) * 16 + boff] : 0.0;
+            asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                         : "+d"(c0), "+d"(c1) : "d"(x[u]), "d"(q0));
+            if (b + u + 1 < lb1) {
+              const double q1 = bvalid ? q_s[(size_t)(b + u + 1) * 16 + boff] : 0.0;
+              asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                           : "+d"(e0), "+d"(e1) : "d"(x[u + 1]), "d"(q1));
+            }
+          }
         }
       }
       c0 += e0;
@@ -171,11 +189,8 @@ __global__ void __launch_bounds__(TMA_THREADS, 2)
         }
       }
     }
-    __syncthreads();                                        // every warp is done with stage s
-    if (threadIdx.x == 0) {
-      const int gn = g + TMA_NSTAGE * gridDim.x;
-      if (gn < ngroups) issue(gn, s);
-    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&empty[s]);                 // this warp is done with stage s
   }
 }
 
@@ -184,7 +199,7 @@ template <int R, int DH> static cudaError_t launch_tma_t(int ngroups, const int2
                                                          int sms, cudaStream_t stream) {
   constexpr int BT = SPMV_GROUP_BLOCKS;
   const size_t smem = (size_t)TMA_NSTAGE * BT * 128 + (size_t)TMA_NSTAGE * (BT + 8) * 4 + (size_t)TMA_NSTAGE * (BT + 12) * 4 +
-                      TMA_NSTAGE * 8 + 128;
+                      2 * TMA_NSTAGE * 8 + 128;
   static bool attr_set[64] = {};
   int dev = 0;
   cudaGetDevice(&dev);
