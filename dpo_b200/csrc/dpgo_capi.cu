@@ -109,12 +109,37 @@ cudaError_t run_spmv(const dpgo_problem *p, const double *X, const double *G, do
   return dpgo::launch_spmv(p->r, p->dh, p->n, p->d_rowptr, p->d_bcol, p->d_bval, X, G, out, p->stream);
 }
 
-int check_precond(const dpgo_problem *p, int precond) {
+// The dense inverse (Q + 0.1 I)^-1 is built on first use (one-shot: scatter block-CSR into N x N in HBM, blocked
+// Gauss-Jordan in place) -- problems that are only evaluated (e.g. the drivers' centralised problem) never pay for it.
+int ensure_dense(dpgo_problem *p) {
+  if (p->d_pinv) return DPGO_OK;
+  if (!(p->precond_mask & (1u << DPGO_PRECOND_DENSE_EXACT)))
+    return fail(DPGO_ERR_STATE, "dense exact preconditioner was not requested in set_Q (precond_mask)");
+  const size_t N = (size_t)p->N;
+  if (N * N * sizeof(double) > (size_t)48 << 30)
+    return fail(DPGO_ERR_UNSUPPORTED, "dense exact preconditioner limited to N^2*8 <= 48 GiB; use block-Jacobi");
+  p->dense_per = (int)((N + p->grid - 1) / p->grid);
+  if (p->dense_per > dpgo::DENSE_PER_MAX)
+    return fail(DPGO_ERR_UNSUPPORTED, "dense exact preconditioner: N too large for the per-CTA slab; use block-Jacobi");
+  DPGO_CUDA(cudaMalloc(&p->d_dense_part, sizeof(double) * (size_t)p->grid * p->r * N));
+  DPGO_CUDA(cudaMalloc(&p->d_pinv, N * N * sizeof(double)));
+  DPGO_CUDA(cudaMemsetAsync(p->d_pinv, 0, N * N * sizeof(double), p->stream));
+  cudaError_t e = dpgo::launch_bsr_to_dense(p->n, p->dh, p->nb, p->d_rowptr, p->d_bcol, p->d_bval, 0.1, p->d_pinv, p->N,
+                                            p->stream);
+  if (e == cudaSuccess) e = dpgo::dense_spd_inverse(p->d_pinv, p->N, p->stream);
+  if (e != cudaSuccess) {
+    free_dev(p->d_pinv);
+    free_dev(p->d_dense_part);
+    return fail(DPGO_ERR_CUDA, std::string("dense preconditioner setup: ") + cudaGetErrorString(e));
+  }
+  return DPGO_OK;
+}
+
+int check_precond(dpgo_problem *p, int precond) {
   if (precond < 0 || precond > 2) return fail(DPGO_ERR_INVALID_ARG, "unknown preconditioner id");
   if (precond == DPGO_PRECOND_BLOCK_JACOBI && !p->d_dinv)
     return fail(DPGO_ERR_STATE, "block-Jacobi preconditioner was not prepared by set_Q (precond_mask)");
-  if (precond == DPGO_PRECOND_DENSE_EXACT && !p->d_pinv)
-    return fail(DPGO_ERR_STATE, "dense exact preconditioner was not prepared by set_Q (precond_mask)");
+  if (precond == DPGO_PRECOND_DENSE_EXACT) return ensure_dense(p);
   return DPGO_OK;
 }
 
@@ -264,61 +289,6 @@ int build_from_triplets(dpgo_problem *p, std::vector<BlockTriplet> &trip, unsign
   p->grid = grid;
   p->precond_mask = precond_mask;
 
-  if (dense) {
-    const size_t N = (size_t)p->N;
-    if (N * N * sizeof(double) > (size_t)48 << 30)
-      return fail(DPGO_ERR_UNSUPPORTED, "dense exact preconditioner limited to N^2*8 <= 48 GiB; use block-Jacobi");
-    p->dense_per = (int)((N + grid - 1) / grid);
-    if (p->dense_per > dpgo::DENSE_PER_MAX)
-      return fail(DPGO_ERR_UNSUPPORTED, "dense exact preconditioner: N too large for the per-CTA slab; use block-Jacobi");
-    DPGO_CUDA(cudaMalloc(&p->d_dense_part, sizeof(double) * (size_t)grid * p->r * N));
-    DPGO_CUDA(cudaMalloc(&p->d_pinv, N * N * sizeof(double)));
-    DPGO_CUDA(cudaMemsetAsync(p->d_pinv, 0, N * N * sizeof(double), p->stream));
-    // scatter Q + 0.1 I into the dense buffer on the host side of a staging copy would cost N^2 of
-    // PCIe traffic; instead scatter block rows with small strided copies: one cudaMemcpy2DAsync per
-    // block would be too many calls, so build per-column strips on the host for only the nonzeros.
-    // Simple and bounded: upload (row, col, val) scalar triplets and scatter with a kernel.
-    std::vector<int> trow, tcol;
-    std::vector<double> tval;
-    trow.reserve((size_t)nb * dh * dh + N);
-    tcol.reserve((size_t)nb * dh * dh + N);
-    tval.reserve((size_t)nb * dh * dh + N);
-    for (int j = 0; j < n; ++j)
-      for (int b = rowptr[j]; b < rowptr[j + 1]; ++b) {
-        const int i = bcol[b];
-        for (int k = 0; k < dh; ++k)
-          for (int c = 0; c < dh; ++c) {
-            double v = bval[(size_t)b * 16 + k * 4 + c];
-            if (i == j && k == c) v += 0.1;
-            trow.push_back(dh * i + k);
-            tcol.push_back(dh * j + c);
-            tval.push_back(v);
-          }
-      }
-    // poses with no diagonal block at all (isolated) still need the 0.1 shift
-    {
-      std::vector<char> has_diag(n, 0);
-      for (int j = 0; j < n; ++j)
-        for (int b = rowptr[j]; b < rowptr[j + 1]; ++b)
-          if (bcol[b] == j) has_diag[j] = 1;
-      for (int j = 0; j < n; ++j)
-        if (!has_diag[j])
-          for (int k = 0; k < dh; ++k) { trow.push_back(dh * j + k); tcol.push_back(dh * j + k); tval.push_back(0.1); }
-    }
-    int *d_tr = nullptr, *d_tc = nullptr;
-    double *d_tv = nullptr;
-    const size_t nt = tval.size();
-    DPGO_CUDA(cudaMalloc(&d_tr, sizeof(int) * nt));
-    DPGO_CUDA(cudaMalloc(&d_tc, sizeof(int) * nt));
-    DPGO_CUDA(cudaMalloc(&d_tv, sizeof(double) * nt));
-    DPGO_CUDA(cudaMemcpyAsync(d_tr, trow.data(), sizeof(int) * nt, cudaMemcpyHostToDevice, p->stream));
-    DPGO_CUDA(cudaMemcpyAsync(d_tc, tcol.data(), sizeof(int) * nt, cudaMemcpyHostToDevice, p->stream));
-    DPGO_CUDA(cudaMemcpyAsync(d_tv, tval.data(), sizeof(double) * nt, cudaMemcpyHostToDevice, p->stream));
-    cudaError_t e = dpgo::launch_scatter_dense(d_tr, d_tc, d_tv, (int64_t)nt, p->d_pinv, p->N, p->stream);
-    if (e == cudaSuccess) e = dpgo::dense_spd_inverse(p->d_pinv, p->N, p->stream);
-    cudaFree(d_tr); cudaFree(d_tc); cudaFree(d_tv);
-    if (e != cudaSuccess) return fail(DPGO_ERR_CUDA, std::string("dense preconditioner setup: ") + cudaGetErrorString(e));
-  }
   p->have_Q = true;
   return DPGO_OK;
 }
@@ -657,7 +627,7 @@ int dpgo_manifold_project(dpgo_problem_t *p, const double *M_host, double *out_h
 }
 
 // ---- optimiser -----------------------------------------------------------------------------------
-static int check_params(const dpgo_problem_t *p, const dpgo_opt_params_t *prm) {
+static int check_params(dpgo_problem_t *p, const dpgo_opt_params_t *prm) {
   DPGO_REQUIRE(prm, DPGO_ERR_INVALID_ARG, "null params");
   DPGO_REQUIRE(prm->algorithm == DPGO_ALG_RTR || prm->algorithm == DPGO_ALG_RGD, DPGO_ERR_INVALID_ARG, "unknown algorithm");
   DPGO_REQUIRE(prm->tr_iterations >= 1 && prm->tr_max_inner >= 1, DPGO_ERR_INVALID_ARG, "iteration counts must be >= 1");

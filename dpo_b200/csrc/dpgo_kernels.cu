@@ -853,6 +853,35 @@ __global__ void k_scatter_dense(const int *__restrict__ row, const int *__restri
   if (t < count) A[(size_t)row[t] + (size_t)N * col[t]] = val[t];
 }
 
+// dense A <- block-CSR Q (+ shift * I): one thread per (block, entry); the output tile of block b is found by
+// binary search in rowptr.  A[(dh*i + k) + N*(dh*j + c)] = bval[b][k][c] with i = bcol[b], j = row of b.
+__global__ void k_bsr_to_dense(int n, int dh, int64_t nb, const int *__restrict__ rowptr, const int *__restrict__ bcol,
+                               const double *__restrict__ bval, double *__restrict__ A, int N) {
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= nb * 16) return;
+  const int64_t b = t >> 4;
+  const int k = (int)((t >> 2) & 3), c = (int)(t & 3);
+  if (k >= dh || c >= dh) return;
+  int lo = 0, hi = n;                 // largest j with rowptr[j] <= b
+  while (hi - lo > 1) {
+    const int mid = (lo + hi) >> 1;
+    if (rowptr[mid] <= b) lo = mid; else hi = mid;
+  }
+  const int j = lo, i = bcol[b];
+  A[(size_t)(dh * i + k) + (size_t)N * (dh * j + c)] = bval[t];
+}
+__global__ void k_add_diag(double *__restrict__ A, int N, double shift) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < N) A[(size_t)t * N + t] += shift;
+}
+
+cudaError_t launch_bsr_to_dense(int n, int dh, int64_t nb, const int *rowptr, const int *bcol, const double *bval,
+                                double shift, double *A, int N, cudaStream_t stream) {
+  if (nb > 0) k_bsr_to_dense<<<(unsigned)((nb * 16 + 255) / 256), 256, 0, stream>>>(n, dh, nb, rowptr, bcol, bval, A, N);
+  k_add_diag<<<(N + 255) / 256, 256, 0, stream>>>(A, N, shift);
+  return cudaGetLastError();
+}
+
 cudaError_t launch_scatter_dense(const int *row, const int *col, const double *val, int64_t count, double *A, int N,
                                  cudaStream_t stream) {
   if (count <= 0) return cudaSuccess;

@@ -70,6 +70,8 @@ cudaError_t launch_pack_tiles(int ts, int count, const int *pose, const double *
 cudaError_t launch_build_G(int r, int dh, int nposes, const int *pose_ids, const int *pose_ptr, const int *edge_slot,
                            const int *edge_out, const double *edge_T, const double *edge_om, const double *gathered,
                            double *G, cudaStream_t stream);
+cudaError_t launch_bsr_to_dense(int n, int dh, int64_t nb, const int *rowptr, const int *bcol, const double *bval,
+                                double shift, double *A, int N, cudaStream_t stream);
 cudaError_t launch_scatter_dense(const int *row, const int *col, const double *val, int64_t count, double *A, int N,
                                  cudaStream_t stream);
 
