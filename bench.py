@@ -116,8 +116,22 @@ def cpu_reference_steps(steps: int, warmup: int, sample_desc_only: bool = False)
     Q = orc.construct_connection_laplacian(meas, n)
     X0 = orc.fixed_stiefel_variable(meas.d, RANK_R) @ orc.chordal_initialization(meas, n)
     if have_port:
-        runner = cpu_port.Runner(Q, n, meas.d, RANK_R)
-        kind, cores, label = "port", runner.threads, "C++ restatement (scalar CSR + sparse Cholesky + RTR), g++ -O3 -march=native"
+        # single thread = the reference's default (ENABLE_OPENMP OFF; Eigen's dense*sparse product is serial);
+        # a threaded variant (products over columns) is tried as well and the faster one is reported
+        runner = cpu_port.Runner(Q, n, meas.d, RANK_R, threads=1)
+        best = 1
+        try:
+            t0 = time.perf_counter(); runner.step(X0); runner.step(X0); t1 = time.perf_counter() - t0
+            nthr = max(2, min(8, os.cpu_count() or 2))
+            alt = cpu_port.Runner(Q, n, meas.d, RANK_R, threads=nthr)
+            t0 = time.perf_counter(); alt.step(X0); alt.step(X0); t2 = time.perf_counter() - t0
+            if t2 < 0.9 * t1:
+                runner, best = alt, nthr
+        except Exception:
+            pass
+        kind, cores = "port", best
+        label = ("C++ restatement of the reference path (scalar-CSR X*Q, min-degree sparse LDL^T solves of Q+0.1I, "
+                 "ROPTLIB RTR/tCG restated; 10+j products per call), g++ -O3")
     else:
         prob = orc.QuadraticProblem(n, meas.d, RANK_R)
         prob.set_Q(Q)
