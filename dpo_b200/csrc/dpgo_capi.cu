@@ -708,6 +708,33 @@ int dpgo_optimize_result(dpgo_problem_t *p, dpgo_opt_result_t *result) {
   return DPGO_OK;
 }
 
+int dpgo_debug_phase_latency(dpgo_problem_t *p, int phases, double *us_per_phase, double *us_launch) {
+  DPGO_CHECK_HANDLE(p);
+  DPGO_REQUIRE(phases >= 1 && us_per_phase, DPGO_ERR_INVALID_ARG, "bad arguments");
+  dpgo_opt_params_t prm;
+  dpgo_opt_params_default(&prm);
+  prm.precond = DPGO_PRECOND_NONE;
+  cudaEvent_t e0, e1;
+  DPGO_CUDA(cudaEventCreate(&e0));
+  DPGO_CUDA(cudaEventCreate(&e1));
+  float ms[2] = {0, 0};
+  const int counts[2] = {1, phases + 1};
+  for (int rep = 0; rep < 2; ++rep) {
+    prm.tr_max_inner = counts[rep];
+    for (int w = 0; w < 3; ++w) DPGO_TRY(run_op(p, dpgo::OP_PHASE_BENCH, prm));
+    DPGO_CUDA(cudaEventRecord(e0, p->stream));
+    for (int w = 0; w < 10; ++w) DPGO_TRY(run_op(p, dpgo::OP_PHASE_BENCH, prm));
+    DPGO_CUDA(cudaEventRecord(e1, p->stream));
+    DPGO_CUDA(cudaEventSynchronize(e1));
+    DPGO_CUDA(cudaEventElapsedTime(&ms[rep], e0, e1));
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  *us_per_phase = 1e3 * (ms[1] - ms[0]) / 10.0 / phases;
+  if (us_launch) *us_launch = 1e3 * ms[0] / 10.0 - *us_per_phase;
+  return DPGO_OK;
+}
+
 int dpgo_spmv_device(dpgo_problem_t *p, const double *X_dev, double *out_dev, int add_G) {
   DPGO_CHECK_HANDLE(p);
   DPGO_REQUIRE(X_dev && out_dev, DPGO_ERR_INVALID_ARG, "null argument");

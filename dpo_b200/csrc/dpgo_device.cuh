@@ -30,6 +30,12 @@ __device__ __forceinline__ int ld_const(const int *p) { return __ldg(p); }
 __device__ __forceinline__ double2 ld_const2(const double *p) {
   return __ldg(reinterpret_cast<const double2 *>(p));
 }
+// Read-once streams (the dense preconditioner): no L1 allocation
+__device__ __forceinline__ double ld_stream(const double *p) {
+  double v;
+  asm volatile("ld.global.nc.L1::no_allocate.f64 %0, [%1];" : "=d"(v) : "l"(p));
+  return v;
+}
 // Vectors that other SMs rewrite between phases of the persistent kernel: L2-only (ld.global.cg)
 // so no stale L1 line can be observed after a grid barrier.
 template <bool COHERENT> __device__ __forceinline__ double ld_vec(const double *p) {
@@ -213,10 +219,9 @@ __device__ __forceinline__ void grid_barrier(unsigned *counter, unsigned &epoch)
   __syncthreads();
   epoch += gridDim.x;
   if (threadIdx.x == 0) {
-    __threadfence();
-    atomicAdd(counter, 1u);
+    // release: every write of this CTA (ordered before by the bar.sync above) becomes visible at gpu scope
+    asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(counter) : "memory");
     while ((int)(ld_acquire_u32(counter) - epoch) < 0) { }
-    __threadfence();
   }
   __syncthreads();
 }

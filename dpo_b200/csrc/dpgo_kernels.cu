@@ -26,34 +26,42 @@ struct BlockCtx {
   int parity;
 };
 
+template <int NUSED = NRED>
 __device__ __forceinline__ void phase_end(const KParams &kp, BlockCtx &bc, double (&acc)[NRED]) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
 #pragma unroll
-  for (int q = 0; q < NRED; ++q) {
+  for (int q = 0; q < NUSED; ++q) {
     double v = warp_sum(acc[q]);
     if (lane == 0) bc.sm_warp[warp * NRED + q] = v;
   }
-  __syncthreads();
+  if (NUSED > 0) __syncthreads();
   double *slot = kp.partials + (size_t)bc.parity * kp.grid * NRED;
-  if (threadIdx.x < NRED) {
+  if ((int)threadIdx.x < NUSED) {
     double s = 0.0;
     for (int w = 0; w < nwarps; ++w) s += bc.sm_warp[w * NRED + threadIdx.x];
     slot[(size_t)blockIdx.x * NRED + threadIdx.x] = s;
   }
   grid_barrier(kp.bar_counter, bc.epoch);
-  if (warp == 0) {
+  if (NUSED > 0) {
+    if (warp == 0) {
+      double s[NUSED > 0 ? NUSED : 1];
 #pragma unroll
-    for (int q = 0; q < NRED; ++q) {
-      double s = 0.0;
-      for (int c = lane; c < kp.grid; c += 32) s += __ldcg(slot + (size_t)c * NRED + q);
-      s = warp_sum(s);
-      if (lane == 0) bc.sm_out[q] = s;
+      for (int q = 0; q < NUSED; ++q) s[q] = 0.0;
+      for (int c = lane; c < kp.grid; c += 32) {
+#pragma unroll
+        for (int q = 0; q < NUSED; ++q) s[q] += __ldcg(slot + (size_t)c * NRED + q);
+      }
+#pragma unroll
+      for (int q = 0; q < NUSED; ++q) {
+        const double t = warp_sum(s[q]);
+        if (lane == 0) bc.sm_out[q] = t;
+      }
     }
-  }
-  __syncthreads();
+    __syncthreads();
 #pragma unroll
-  for (int q = 0; q < NRED; ++q) acc[q] = bc.sm_out[q];
-  __syncthreads();           // sm_out / sm_warp may be rewritten by the next phase
+    for (int q = 0; q < NUSED; ++q) acc[q] = bc.sm_out[q];
+    __syncthreads();           // sm_out / sm_warp may be rewritten by the next phase
+  }
   bc.parity ^= 1;
 }
 
@@ -257,17 +265,26 @@ template <int R> __device__ void phase_dense(const KParams &kp, const double *V,
 #pragma unroll
     for (int a = 0; a < R; ++a) acc[a] = 0.0;
     int kk = 0;
-    for (; kk + 8 <= nk; kk += 8) {
-      double p[8];
+    for (; kk + 16 <= nk; kk += 16) {
+      double p[16];
 #pragma unroll
-      for (int u = 0; u < 8; ++u) p[u] = ld_const(P + (size_t)(kk + u) * N + c);
+      for (int u = 0; u < 16; ++u) p[u] = ld_stream(P + (size_t)(kk + u) * N + c);
 #pragma unroll
-      for (int u = 0; u < 8; ++u)
+      for (int u = 0; u < 16; ++u)
+#pragma unroll
+        for (int a = 0; a < R; ++a) acc[a] = fma(sV[(kk + u) * R + a], p[u], acc[a]);
+    }
+    for (; kk + 4 <= nk; kk += 4) {
+      double p[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) p[u] = ld_stream(P + (size_t)(kk + u) * N + c);
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
 #pragma unroll
         for (int a = 0; a < R; ++a) acc[a] = fma(sV[(kk + u) * R + a], p[u], acc[a]);
     }
     for (; kk < nk; ++kk) {
-      const double p = ld_const(P + (size_t)kk * N + c);
+      const double p = ld_stream(P + (size_t)kk * N + c);
 #pragma unroll
       for (int a = 0; a < R; ++a) acc[a] = fma(sV[kk * R + a], p, acc[a]);
     }
@@ -408,12 +425,17 @@ template <int R, int DH> __global__ void __launch_bounds__(OPT_THREADS, 1) k_opt
   int cur = 0;   // which X buffer holds the current iterate
 
   // ---- single-operation entry points -------------------------------------------------------
+  if (kp.op == OP_PHASE_BENCH) {          // diagnostic: tr_max_inner empty phases (barrier + 1-scalar reduction)
+    for (int i = 0; i < prm.tr_max_inner; ++i) { zero(acc); acc[0] = 1.0; phase_end<1>(kp, bc, acc); }
+    if (blockIdx.x == 0 && threadIdx.x == 0) { res.f_init = acc[0]; *kp.result = res; *kp.bar_epoch = bc.epoch; }
+    return;
+  }
   if (kp.op == OP_PRECON) {
     if (precond == DPGO_PRECOND_DENSE_EXACT) {
       phase_dense<R>(kp, kp.v[V_AUX], sV);
-      zero(acc); phase_end(kp, bc, acc);
+      zero(acc); phase_end<0>(kp, bc, acc);
       zero(acc); phase_pz<R, DH>(kp, 0, kp.v[V_AUX], kp.v[V_Z], acc);
-      phase_end(kp, bc, acc);
+      phase_end<1>(kp, bc, acc);
     } else {
       // reuse phase_update with res := AUX (first = false, alpha = 0 would need RES); do it directly
       constexpr int TS = R * DH;
@@ -500,9 +522,9 @@ template <int R, int DH> __global__ void __launch_bounds__(OPT_THREADS, 1) k_opt
       // -- z0 = M^-1 g for the dense preconditioner (pose-local ones were fused into phase E)
       if (!z0_valid) {
         phase_dense<R>(kp, kp.v[V_RG0 + cb], sV);
-        zero(acc); phase_end(kp, bc, acc);
+        zero(acc); phase_end<0>(kp, bc, acc);
         zero(acc); phase_pz<R, DH>(kp, cb, kp.v[V_RG0 + cb], kp.v[V_Z00 + cb], acc);
-        phase_end(kp, bc, acc);
+        phase_end<1>(kp, bc, acc);
         zr0 = acc[0];
         z0_valid = true;
       }
@@ -520,7 +542,7 @@ template <int R, int DH> __global__ void __launch_bounds__(OPT_THREADS, 1) k_opt
         double *dnew = kp.v[V_D0 + (1 - pd)];
         zero(acc);
         phase_hess<R, DH>(kp, cb, zsrc, kp.v[V_D0 + pd], dnew, beta, true, acc);
-        phase_end(kp, bc, acc);
+        phase_end<1>(kp, bc, acc);
         res.spmv_passes++;
         res.tcg_iterations++;
         pd = 1 - pd;
@@ -536,7 +558,7 @@ template <int R, int DH> __global__ void __launch_bounds__(OPT_THREADS, 1) k_opt
         e_Pe = e_new;
         zero(acc);
         phase_update<R, DH>(kp, cb, dcur, alpha, eta_zero, precond, acc);
-        phase_end(kp, bc, acc);
+        phase_end<2>(kp, bc, acc);
         eta_zero = false;
         const double nr = sqrt(acc[0]);
         const double n0t = n0;                         // n0^theta, theta = 1
@@ -547,9 +569,9 @@ template <int R, int DH> __global__ void __launch_bounds__(OPT_THREADS, 1) k_opt
         double zr_new = acc[1];
         if (precond == DPGO_PRECOND_DENSE_EXACT) {
           phase_dense<R>(kp, kp.v[V_RES], sV);
-          zero(acc); phase_end(kp, bc, acc);
+          zero(acc); phase_end<0>(kp, bc, acc);
           zero(acc); phase_pz<R, DH>(kp, cb, kp.v[V_RES], kp.v[V_Z], acc);
-          phase_end(kp, bc, acc);
+          phase_end<1>(kp, bc, acc);
           zr_new = acc[0];
         }
         res.precond_applies++;
@@ -564,7 +586,7 @@ template <int R, int DH> __global__ void __launch_bounds__(OPT_THREADS, 1) k_opt
       // -- candidate point, model decrease, actual decrease
       zero(acc);
       phase_retract<R, DH>(kp, cb, 0, dcur, tau, eta_zero, 0.0, acc);
-      phase_end(kp, bc, acc);
+      phase_end<2>(kp, bc, acc);
       const double denom = -acc[0] - 0.5 * acc[1];
       zero(acc);
       phase_eval<R, DH>(kp, 1 - cb, false, precond, acc);
@@ -604,7 +626,7 @@ template <int R, int DH> __global__ void __launch_bounds__(OPT_THREADS, 1) k_opt
 
   zero(acc);
   phase_final<R, DH>(kp, cur, acc);
-  phase_end(kp, bc, acc);
+  phase_end<1>(kp, bc, acc);
   res.relative_change = sqrt(acc[0] / (double)kp.n);
   res.success = 1;
   if (blockIdx.x == 0 && threadIdx.x == 0) { *kp.result = res; *kp.bar_epoch = bc.epoch; }

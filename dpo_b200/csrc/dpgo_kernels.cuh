@@ -27,6 +27,7 @@ enum OpCode {
   OP_RHESS = 2,      // HD = Hess f(X0)[AUX]
   OP_PRECON = 3,     // Z  = P_X0( M^-1 AUX )
   OP_RETRACT = 4,    // X1 = R_X0(AUX)
+  OP_PHASE_BENCH = 9, // diagnostic: empty phases
 };
 
 constexpr int NRED = 4;            // scalars reduced per phase

@@ -182,6 +182,8 @@ DPGO_API int dpgo_optimize_result(dpgo_problem_t *p, dpgo_opt_result_t *result);
 /* the Q.X product kernel alone on device buffers (the roofline kernel): Out = X Q (+ G) */
 DPGO_API int dpgo_spmv_device(dpgo_problem_t *p, const double *X_dev, double *out_dev, int add_G);
 DPGO_API int64_t dpgo_spmv_algorithmic_bytes(const dpgo_problem_t *p, int add_G);
+/* diagnostic: cost of one empty phase of the persistent kernel (grid barrier + scalar reduction) and of its launch */
+DPGO_API int dpgo_debug_phase_latency(dpgo_problem_t *p, int phases, double *us_per_phase, double *us_launch);
 
 /* ---- boundary-pose exchange (multi-agent, one agent per GPU) ----------------------------- */
 /* ref: PGOAgent::getSharedPoseDict, src/PGOAgent.cpp:95-105: register which local poses are
