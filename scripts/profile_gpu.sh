@@ -5,7 +5,7 @@
 set -x
 mkdir -p gpurun_out
 TAG=${1:-r01}
-ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/launches_${TAG}.csv \
+ncu --metrics gpu__time_duration.sum --clock-control none -k regex:"k_(optimize|spmv|pack|build|stiefel)" -c 400 --csv --log-file gpurun_out/launches_${TAG}.csv \
     python bench.py --steps 12 --warmup 3 --no-cpu > gpurun_out/bench_under_ncu_${TAG}.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:k_spmv -s 3 -c 2 -f -o gpurun_out/prof_spmv_${TAG} \
     python bench.py --steps 6 --warmup 3 --no-cpu > gpurun_out/ncu_spmv_${TAG}.log 2>&1
