@@ -350,7 +350,7 @@ def run_gpu_arm(args):
     else:
         run = DistributedPGO(edges, n, world, r=RANK_R, schedule="coloured", X_init=X0, rank=rank, world=world,
                              device=local_rank, dist=dist)
-        ag = run.agents[rank]
+        ag = run.agents[rank]          # world == number of agents here: one agent per GPU
         dh = d + 1
         cols = (run.glob[rank][:, None] * dh + np.arange(dh)[None, :]).ravel()
         X0d = torch.from_numpy(np.asfortranarray(X0[:, cols]).ravel(order="F").copy()).to(dev)

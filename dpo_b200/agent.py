@@ -393,8 +393,9 @@ class DistributedPGO:
         self.k, self.n, self.r, self.d = k, n, r, edges.d
         self.rank = rank
         self.distributed = dist is not None and world is not None and world > 1
+        self.world = world if self.distributed else 1
         if self.distributed:
-            assert world == k, "one agent per rank"
+            assert k % world == 0, "agents must divide evenly over the ranks (contiguous blocks of k/world agents)"
         self.owner = contiguous_owner(n, k) if owner is None else np.asarray(owner, dtype=np.int64)
         parts, counts, glob = partition_edges(edges, self.owner, k)
         self.counts, self.glob = counts, glob
@@ -404,7 +405,8 @@ class DistributedPGO:
         self.schedule = schedule
         if X_init is None:
             X_init = pg.fixedStiefelVariable(self.d, r) @ pg.chordalInitialization(self.d, n, edges)
-        self.local_ids = [rank] if self.distributed else list(range(k))
+        per_rank = k // self.world
+        self.local_ids = list(range(rank * per_rank, (rank + 1) * per_rank)) if self.distributed else list(range(k))
         self.agents: Dict[int, PGOAgent] = {}
         dh = self.d + 1
         self.dev = torch.device("cuda", device)
@@ -431,10 +433,17 @@ class DistributedPGO:
         ts = r * dh
         self.slot_elems = self.plan.pmax * ts
         self.gathered = torch.zeros(k * self.slot_elems, dtype=torch.float64, device=self.dev)
-        self.send = {a: (self.gathered[a * self.slot_elems:(a + 1) * self.slot_elems] if not self.distributed
-                         else torch.zeros(self.slot_elems, dtype=torch.float64, device=self.dev))
-                     for a in self.local_ids}
-        self.stats_local = torch.zeros(4, dtype=torch.float64, device=self.dev)
+        # agents are laid out in agent order in the gathered buffer; a rank owns a contiguous run of them, so its
+        # send buffer is one contiguous piece (rank-major all-gather order == agent order)
+        if self.distributed:
+            self.send_all = torch.zeros(per_rank * self.slot_elems, dtype=torch.float64, device=self.dev)
+            base = self.local_ids[0]
+            self.send = {a: self.send_all[(a - base) * self.slot_elems:(a - base + 1) * self.slot_elems]
+                         for a in self.local_ids}
+        else:
+            self.send_all = None
+            self.send = {a: self.gathered[a * self.slot_elems:(a + 1) * self.slot_elems] for a in self.local_ids}
+        self.stats_local = torch.zeros(4 * len(self.local_ids), dtype=torch.float64, device=self.dev)
         self.stats_all = torch.zeros(4 * k, dtype=torch.float64, device=self.dev)
         self.selected = [0]
         self.round = 0
@@ -444,7 +453,7 @@ class DistributedPGO:
         for a in self.local_ids:
             self.agents[a].pack_public(self.send[a].data_ptr())
         if self.distributed:
-            self.dist.all_gather_into_tensor(self.gathered, self.send[self.rank])
+            self.dist.all_gather_into_tensor(self.gathered, self.send_all)
         for a in self.local_ids:
             self.agents[a].build_G(self.gathered.data_ptr(), self.k * self.plan.pmax)
 
@@ -464,7 +473,8 @@ class DistributedPGO:
             vals[a] = res
         if self.distributed:
             t = self.torch
-            self.stats_local.copy_(t.from_numpy(vals[self.rank]))
+            mine = np.ascontiguousarray(vals[self.local_ids[0]:self.local_ids[-1] + 1]).ravel()
+            self.stats_local.copy_(t.from_numpy(mine))
             self.dist.all_gather_into_tensor(self.stats_all, self.stats_local)
             vals = self.stats_all.cpu().numpy().reshape(self.k, 4)
         cost = float(np.sum(vals[:, 0] + vals[:, 1]))          # 2 f_central = sum(<XQ,X> + <X,G>)
