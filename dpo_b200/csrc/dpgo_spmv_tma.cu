@@ -120,66 +120,59 @@ __global__ void __launch_bounds__(TMA_THREADS, 2)
   }
 
   // ---------------- consumers ----------------
-  // One warp per pose tile.  The 4x4 block product runs on the fp64 tensor pipe (mma.sync m8n8k4, SASS DMMA):
-  // the A fragment IS the lane mapping (lane = 4a + k holds P_i[a,k]: one coalesced 8-byte gather per lane covers
-  // the neighbour tile once), the B fragment is one 8-byte shared load per lane (16 lanes cover the 128-byte
-  // block once -> a single smem wavefront), and the accumulator fragment leaves Out_j[a, 2k..2k+1] in lane (a,k),
-  // k < 2 -- no shuffles, no 128-bit smem broadcasts.
-  // Lanes outside the valid fragment (a >= R, or B columns 4..7) read a duplicate of a valid element instead of
-  // being predicated off: they only feed accumulator rows / columns that are never stored, and the padded rows
-  // of a (d=2) block are zero, so no per-lane predicate or select is needed in the inner loop.
   const int a = lane >> 2, k = lane & 3;
-  const int a_ld = (a < R) ? a : (R - 1), k_ld = (k < DH) ? k : (DH - 1);
-  const double *Xl = X + (k_ld * R + a_ld);               // + i * TS
-  const int boff = k * 4 + ((lane >> 2) & 3);             // B[k][n] = bval[k*4 + n], columns n >= 4 mirror n & 3
+  const bool valid = (a < R) && (k < DH);
+  const int off = k * R + a;
+  const int bn = lane >> 2;                            // B fragment: column n = lane>>2, row k = lane&3
+  const bool bvalid = bn < 4;
+  const int boff = k * 4 + bn;
   int it = 0;
   for (int g = blockIdx.x; g < ngroups; g += gridDim.x, ++it) {
     const int s = it % TMA_NSTAGE;
     mbar_wait(&full[s], (unsigned)((it / TMA_NSTAGE) & 1));
     const int2 g0 = __ldg(gi + g), g1 = __ldg(gi + g + 1);
     const int r0 = g0.x, r1 = g1.x, b0 = g0.y;
-    const double *q_s = sq + (size_t)s * BT * 16 + boff;
+    const double *q_s = sq + (size_t)s * BT * 16;
     const int *idx_s = sidx + s * IDX_CAP + (b0 - (b0 & ~3));
     const int *rp_s = srp + s * RP_CAP + (r0 - (r0 & ~3));
-    // the starting warp rotates with the group so that short groups load all warps evenly
+
+    // One warp per pose tile.  The 4x4 block product runs on the fp64 tensor pipe (mma.sync m8n8k4, SASS DMMA):
+    // the A fragment IS the lane mapping (lane = 4a + k holds P_i[a,k]), the B fragment is one 8-byte shared
+    // load per lane (lanes 0..15 cover the 128-byte block exactly once -> a single smem wavefront), and the
+    // accumulator fragment leaves Out_j[a, 2k..2k+1] in lane (a,k), k < 2 -- no shuffles, no 128-bit smem
+    // broadcasts.  The starting warp rotates with the group so that short groups load all warps evenly.
     const int wrot = (warp + it * 7) % NCONS;
     for (int j = r0 + wrot; j < r1; j += NCONS) {
       const int lb0 = rp_s[j - r0] - b0, lb1 = rp_s[j - r0 + 1] - b0;
-      double c0 = 0.0, c1 = 0.0, e0 = 0.0, e1 = 0.0, f0 = 0.0, f1 = 0.0, h0 = 0.0, h1 = 0.0;   // 4 DMMA chains
+      double c0 = 0.0, c1 = 0.0, e0 = 0.0, e1 = 0.0;      // two accumulator pairs (shorter DMMA chains)
       for (int b = lb0; b < lb1; b += SPMV_BATCH) {
-        const int nrem = lb1 - b;                            // warp-uniform
         double x[SPMV_BATCH];
 #pragma unroll
-        for (int u0 = 0; u0 < SPMV_BATCH; u0 += 4) {         // all global gathers of the batch in flight together
-          if (u0 < nrem) {
+        for (int u = 0; u < SPMV_BATCH; u += 2) {          // all global gathers of the batch in flight together
+          if (b + u < lb1) {                                // warp-uniform
+            const int i0 = idx_s[b + u];
+            const bool in1 = (b + u + 1 < lb1);
+            const int i1 = in1 ? idx_s[b + u + 1] : i0;
+            x[u] = valid ? __ldg(X + (size_t)i0 * TS + off) : 0.0;
+            x[u + 1] = (valid && in1) ? __ldg(X + (size_t)i1 * TS + off) : 0.0;
+          }
+        }
 #pragma unroll
-            for (int u = u0; u < u0 + 4; ++u) {
-              x[u] = 0.0;
-              if (u < nrem) x[u] = __ldg(Xl + (size_t)idx_s[b + u] * TS);
+        for (int u = 0; u < SPMV_BATCH; u += 2) {
+          if (b + u < lb1) {
+            const double q0 = bvalid ? q_s[(size_t)(b + u) * 16 + boff] : 0.0;
+            asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                         : "+d"(c0), "+d"(c1) : "d"(x[u]), "d"(q0));
+            if (b + u + 1 < lb1) {
+              const double q1 = bvalid ? q_s[(size_t)(b + u + 1) * 16 + boff] : 0.0;
+              asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                           : "+d"(e0), "+d"(e1) : "d"(x[u + 1]), "d"(q1));
             }
           }
         }
-#pragma unroll
-        for (int u0 = 0; u0 < SPMV_BATCH; u0 += 4) {
-          if (u0 < nrem) {
-            const double *qb = q_s + (size_t)(b + u0) * 16;
-            const double q0 = qb[0];
-            const double q1 = (u0 + 1 < nrem) ? qb[16] : 0.0;
-            const double q2 = (u0 + 2 < nrem) ? qb[32] : 0.0;
-            const double q3 = (u0 + 3 < nrem) ? qb[48] : 0.0;
-            asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
-                         : "+d"(c0), "+d"(c1) : "d"(x[u0]), "d"(q0));
-            asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
-                         : "+d"(e0), "+d"(e1) : "d"(x[u0 + 1]), "d"(q1));
-            asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
-                         : "+d"(f0), "+d"(f1) : "d"(x[u0 + 2]), "d"(q2));
-            asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
-                         : "+d"(h0), "+d"(h1) : "d"(x[u0 + 3]), "d"(q3));
-          }
-        }
       }
-      c0 = (c0 + e0) + (f0 + h0);
-      c1 = (c1 + e1) + (f1 + h1);
+      c0 += e0;
+      c1 += e1;
       // lane (a, k): c0 = Out_j[a, 2k], c1 = Out_j[a, 2k+1]
       if (a < R && k < 2) {
         const int cA = 2 * k, cB = 2 * k + 1;

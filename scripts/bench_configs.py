@@ -56,9 +56,12 @@ def main():
 
     if args.dataset == "synthetic":
         dims = tuple(int(v) for v in args.grid.split(","))
-        edges, n, _ = pg.synthetic_grid_graph(*dims, edges_per_pose=4.0, seed=0)
-        odo = np.flatnonzero(edges.p1 + 1 == edges.p2)
-        T0 = pg.odometryInitialization(3, n, edges.take(odo))
+        edges, n, Tgt = pg.synthetic_grid_graph(*dims, edges_per_pose=4.0, seed=0)
+        # initial guess: ground truth with perturbed translations (a chordal solve of a 100k-pose 3-D lattice is a
+        # separate, one-shot host problem; the odometry chain along the boustrophedon path drifts too far)
+        rng = np.random.default_rng(1)
+        T0 = Tgt.copy()
+        T0.reshape(3, n, 4)[:, :, 3] += 0.3 * rng.standard_normal((3, n))
         label = f"synthetic grid {dims} = {n} poses / {len(edges)} edges"
     else:
         edges, n = pg.read_g2o_file(os.path.join(ROOT, "data", args.dataset + ".g2o"))
