@@ -503,6 +503,49 @@ class DistributedPGO:
                 self.selected = [int(np.argmax(per_agent))]           # ref :308-325
         return RoundStats(cost, gn, active)
 
+    # -- the same round through the HOST-level interface (reference protocol: host matrices in and out) -------
+    def step_host(self) -> None:
+        """One round with every iterate crossing the host boundary, as a user of the reference API would drive it:
+        getSharedPoseDict -> (all-gather of the host-packed public poses) -> updateNeighborPoses -> iterate(), i.e.
+        per active agent H2D of X and G, one persistent kernel, D2H of X.  Used for the end-to-end number."""
+        torch = self.torch
+        dh, ts = self.d + 1, self.r * (self.d + 1)
+        if not hasattr(self, "_host_send"):
+            self._host_send = torch.zeros(len(self.local_ids) * self.slot_elems, dtype=torch.float64).pin_memory()
+            self._host_gath = torch.zeros(self.k * self.slot_elems, dtype=torch.float64).pin_memory()
+        hs = self._host_send.numpy()
+        for li, a in enumerate(self.local_ids):
+            ag = self.agents[a]
+            base = li * self.slot_elems
+            for s, q in enumerate(self.plan.public[a]):
+                hs[base + s * ts: base + (s + 1) * ts] = ag.X[:, q * dh:(q + 1) * dh].ravel(order="F")
+        if self.distributed:
+            self.send_all.copy_(self._host_send, non_blocking=True)
+            self.dist.all_gather_into_tensor(self.gathered, self.send_all)
+            self._host_gath.copy_(self.gathered, non_blocking=False)
+            hg = self._host_gath.numpy()
+        else:
+            hg = hs
+        active = self._active()
+        for a in self.local_ids:
+            if a not in active:
+                continue
+            ag = self.agents[a]
+            for b in self.plan.tables[a]["neighbors"]:
+                poses = {}
+                for s, q in enumerate(self.plan.public[b]):
+                    off = (b * self.plan.pmax + s) * ts
+                    poses[(b, int(q))] = hg[off:off + ts].reshape(self.r, dh, order="F")
+                ag.updateNeighborPoses(b, poses)
+            ag.iterate(True)
+        self.round += 1
+
+    def host_bytes_per_step(self):
+        """(h2d, d2h) bytes one active agent moves per host-level step: X and G in, X out (+ result record)."""
+        a = self.local_ids[0]
+        vb = self.r * (self.d + 1) * int(self.counts[a]) * 8
+        return 2 * vb + self.slot_elems * 8, vb + 112 + self.k * self.slot_elems * 8
+
     def assemble(self) -> np.ndarray:
         """Gather the full iterate on the host (all local agents; distributed: rank-local block only)."""
         dh = self.d + 1
