@@ -293,6 +293,110 @@ template <int R> __device__ void phase_dense(const KParams &kp, const double *V,
   }
 }
 
+// ---- TMA-fed variant of phase_dense -----------------------------------------------------------------------
+// Warp 15 is the producer: it streams the CTA's row slab of Pinv through a DENSE_NST-deep shared-memory ring with
+// 1-D bulk TMA copies (one chunk = one row x DENSE_SEG columns = 15 KB, contiguous in HBM); warps 0..14 consume
+// (thread t owns columns t + 480 m, m < 4, of the current column segment).  ~90 KB in flight per SM, no register
+// staging, so the stream runs close to the copy roofline instead of being limited by loads in flight per thread.
+constexpr int DENSE_NST = 6;
+constexpr int DENSE_CONS = OPT_THREADS - 32;          // 480 consumer threads
+constexpr int DENSE_SEG = DENSE_CONS * 4;             // 1920 columns per chunk
+
+struct DenseRing {
+  double *buf;          // DENSE_NST * DENSE_SEG doubles
+  uint64_t *full;       // DENSE_NST
+  uint64_t *empty;      // DENSE_NST
+  unsigned count;       // chunks issued / consumed so far in this kernel (same in every thread)
+};
+
+__device__ __forceinline__ uint32_t smem_addr(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_wait_parity(uint64_t *bar, unsigned parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "DW_LOOP:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DW_DONE;\n"
+      "bra DW_LOOP;\n"
+      "DW_DONE:\n"
+      "}\n" ::"r"(smem_addr(bar)),
+      "r"(parity)
+      : "memory");
+}
+
+template <int R> __device__ void phase_dense_tma(const KParams &kp, const double *V, double *sV, DenseRing &ring) {
+  const int N = kp.N;
+  const int per = kp.dense_per;
+  const int k0 = min(N, (int)blockIdx.x * per), k1 = min(N, k0 + per);
+  const int nk = k1 - k0;
+  const int nseg = (N + DENSE_SEG - 1) / DENSE_SEG;
+  const unsigned total = (unsigned)(nk > 0 ? nk * nseg : 0);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (nk > 0) {
+    for (int q = threadIdx.x; q < nk * R; q += blockDim.x) sV[q] = __ldcg(V + (size_t)k0 * R + q);
+  }
+  __syncthreads();
+  if (nk > 0) {
+    if (warp == (OPT_THREADS / 32 - 1)) {
+      // ---------------- producer ----------------
+      if (lane == 0) {
+        unsigned c = ring.count;
+        for (int sg = 0; sg < nseg; ++sg) {
+          const int c0 = sg * DENSE_SEG;
+          const unsigned bytes = (unsigned)min(DENSE_SEG, N - c0) * 8u;
+          for (int kk = 0; kk < nk; ++kk, ++c) {
+            const int st = c % DENSE_NST;
+            if (c >= DENSE_NST) mbar_wait_parity(&ring.empty[st], ((c / DENSE_NST) - 1) & 1);
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(&ring.full[st])), "r"(bytes)
+                         : "memory");
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                             smem_addr(ring.buf + (size_t)st * DENSE_SEG)),
+                         "l"(kp.pinv + (size_t)(k0 + kk) * N + c0), "r"(bytes), "r"(smem_addr(&ring.full[st]))
+                         : "memory");
+          }
+        }
+      }
+    } else {
+      // ---------------- consumers ----------------
+      double *part = kp.dense_part + (size_t)blockIdx.x * R * N;
+      unsigned c = ring.count;
+      for (int sg = 0; sg < nseg; ++sg) {
+        const int c0 = sg * DENSE_SEG;
+        double acc[4][R];
+#pragma unroll
+        for (int m = 0; m < 4; ++m)
+#pragma unroll
+          for (int a = 0; a < R; ++a) acc[m][a] = 0.0;
+        for (int kk = 0; kk < nk; ++kk, ++c) {
+          const int st = c % DENSE_NST;
+          mbar_wait_parity(&ring.full[st], (c / DENSE_NST) & 1);
+          const double *sp = ring.buf + (size_t)st * DENSE_SEG + threadIdx.x;
+          double v[R];
+#pragma unroll
+          for (int a = 0; a < R; ++a) v[a] = sV[kk * R + a];
+#pragma unroll
+          for (int m = 0; m < 4; ++m) {
+            const double pv = sp[m * DENSE_CONS];            // columns past N hold stale data, never stored
+#pragma unroll
+            for (int a = 0; a < R; ++a) acc[m][a] = fma(v[a], pv, acc[m][a]);
+          }
+          __syncwarp();
+          if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_addr(&ring.empty[st])) : "memory");
+        }
+#pragma unroll
+        for (int m = 0; m < 4; ++m) {
+          const int col = c0 + (int)threadIdx.x + m * DENSE_CONS;
+          if (col < N) {
+#pragma unroll
+            for (int a = 0; a < R; ++a) part[(size_t)col * R + a] = acc[m][a];
+          }
+        }
+      }
+    }
+  }
+  ring.count += total;
+}
+
 template <int R, int DH>
 __device__ void phase_pz(const KParams &kp, int cb, const double *V, double *Zout, double (&acc)[NRED]) {
   constexpr int TS = R * DH;
@@ -313,6 +417,14 @@ __device__ void phase_pz(const KParams &kp, int cb, const double *V, double *Zou
     if (ld) {
       const double *pp = kp.dense_part + idx;
       int b = 0;
+      // fixed summation order (slab 0, 1, 2, ...) with 16 independent L2 loads in flight per lane
+      for (; b + 16 <= nslabs; b += 16) {
+        double tt[16];
+#pragma unroll
+        for (int u = 0; u < 16; ++u) tt[u] = __ldcg(pp + (size_t)(b + u) * stride);
+#pragma unroll
+        for (int u = 0; u < 16; ++u) t += tt[u];
+      }
       for (; b + 4 <= nslabs; b += 4) {
         const double t0 = __ldcg(pp + (size_t)b * stride), t1 = __ldcg(pp + (size_t)(b + 1) * stride);
         const double t2 = __ldcg(pp + (size_t)(b + 2) * stride), t3 = __ldcg(pp + (size_t)(b + 3) * stride);
@@ -411,6 +523,23 @@ template <int R, int DH> __global__ void __launch_bounds__(OPT_THREADS, 1) k_opt
   bc.sm_warp = smem;
   bc.sm_out = smem + (OPT_THREADS / 32) * NRED;
   double *sV = bc.sm_out + NRED;                // dense-preconditioner staging (dense_per * R doubles)
+  DenseRing ring;
+  ring.buf = sV + (size_t)DENSE_PER_MAX * R;    // 16-byte aligned: every preceding block is a multiple of 2 doubles
+  ring.full = reinterpret_cast<uint64_t *>(ring.buf + (size_t)DENSE_NST * DENSE_SEG);
+  ring.empty = ring.full + DENSE_NST;
+  ring.count = 0;
+  // bulk-TMA streaming needs 16-byte aligned rows (N even) and only pays off for a real stream
+  const bool dense_tma = (kp.pinv != nullptr) && ((kp.N & 1) == 0) && (kp.N >= 2048);
+  if (dense_tma) {
+    if (threadIdx.x == 0) {
+      for (int st = 0; st < DENSE_NST; ++st) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(&ring.full[st])), "r"(1));
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(&ring.empty[st])), "r"(OPT_THREADS / 32 - 1));
+      }
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+  }
   bc.epoch = *kp.bar_epoch;
   bc.parity = 0;
   const dpgo_opt_params_t prm = kp.prm;
@@ -432,7 +561,7 @@ template <int R, int DH> __global__ void __launch_bounds__(OPT_THREADS, 1) k_opt
   }
   if (kp.op == OP_PRECON) {
     if (precond == DPGO_PRECOND_DENSE_EXACT) {
-      phase_dense<R>(kp, kp.v[V_AUX], sV);
+      if (dense_tma) phase_dense_tma<R>(kp, kp.v[V_AUX], sV, ring); else phase_dense<R>(kp, kp.v[V_AUX], sV);
       zero(acc); phase_end<0>(kp, bc, acc);
       zero(acc); phase_pz<R, DH>(kp, 0, kp.v[V_AUX], kp.v[V_Z], acc);
       phase_end<1>(kp, bc, acc);
@@ -521,7 +650,7 @@ template <int R, int DH> __global__ void __launch_bounds__(OPT_THREADS, 1) k_opt
     while (true) {
       // -- z0 = M^-1 g for the dense preconditioner (pose-local ones were fused into phase E)
       if (!z0_valid) {
-        phase_dense<R>(kp, kp.v[V_RG0 + cb], sV);
+        if (dense_tma) phase_dense_tma<R>(kp, kp.v[V_RG0 + cb], sV, ring); else phase_dense<R>(kp, kp.v[V_RG0 + cb], sV);
         zero(acc); phase_end<0>(kp, bc, acc);
         zero(acc); phase_pz<R, DH>(kp, cb, kp.v[V_RG0 + cb], kp.v[V_Z00 + cb], acc);
         phase_end<1>(kp, bc, acc);
@@ -568,7 +697,7 @@ template <int R, int DH> __global__ void __launch_bounds__(OPT_THREADS, 1) k_opt
         }
         double zr_new = acc[1];
         if (precond == DPGO_PRECOND_DENSE_EXACT) {
-          phase_dense<R>(kp, kp.v[V_RES], sV);
+          if (dense_tma) phase_dense_tma<R>(kp, kp.v[V_RES], sV, ring); else phase_dense<R>(kp, kp.v[V_RES], sV);
           zero(acc); phase_end<0>(kp, bc, acc);
           zero(acc); phase_pz<R, DH>(kp, cb, kp.v[V_RES], kp.v[V_Z], acc);
           phase_end<1>(kp, bc, acc);
@@ -784,7 +913,7 @@ __global__ void k_build_G(int nposes, const int *__restrict__ pose_ids, const in
 // launchers
 // ---------------------------------------------------------------------------------------------
 template <int R, int DH> static cudaError_t launch_optimize_t(const KParams &kp, cudaStream_t stream) {
-  const size_t smem = ((OPT_THREADS / 32) * NRED + NRED + (size_t)DENSE_PER_MAX * R) * sizeof(double);
+  const size_t smem = ((OPT_THREADS / 32) * NRED + NRED + (size_t)DENSE_PER_MAX * R + (size_t)DENSE_NST * DENSE_SEG + 2 * DENSE_NST) * sizeof(double);
   static bool attr_set[64] = {};
   int dev = 0;
   cudaGetDevice(&dev);
@@ -798,7 +927,7 @@ template <int R, int DH> static cudaError_t launch_optimize_t(const KParams &kp,
 }
 
 template <int R, int DH> static int max_grid_t(int device) {
-  const size_t smem = ((OPT_THREADS / 32) * NRED + NRED + (size_t)DENSE_PER_MAX * R) * sizeof(double);
+  const size_t smem = ((OPT_THREADS / 32) * NRED + NRED + (size_t)DENSE_PER_MAX * R + (size_t)DENSE_NST * DENSE_SEG + 2 * DENSE_NST) * sizeof(double);
   cudaFuncSetAttribute(k_optimize<R, DH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   int per_sm = 0, sms = 0;
   if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_optimize<R, DH>, OPT_THREADS, smem) != cudaSuccess) return 0;
