@@ -118,6 +118,20 @@ def build_cpp_program(sources, output, defines=(), extra_includes=()):
     return output
 
 
+EXAMPLES_DIR = os.path.join(HERE, "..", "examples")
+EXAMPLES_BIN = os.path.join(HERE, "..", "build", "examples")
+
+
+def build_examples():
+    """Our own C++ drivers (examples/*.cpp) against libDPGO.so."""
+    out = []
+    for f in sorted(os.listdir(EXAMPLES_DIR)):
+        if f.endswith(".cpp"):
+            out.append(build_cpp_program([os.path.join(EXAMPLES_DIR, f)],
+                                         os.path.abspath(os.path.join(EXAMPLES_BIN, f[:-4]))))
+    return out
+
+
 REFERENCE = "/root/reference"
 REF_BUILD = os.path.join(HERE, "..", "build", "ref")
 
@@ -147,5 +161,5 @@ def build_reference_drivers():
 if __name__ == "__main__":
     print(build_library(force="--force" in sys.argv, verbose=True))
     print(build_host(force="--force" in sys.argv))
-    for b in build_reference_drivers():
+    for b in build_examples() + build_reference_drivers():
         print(b)

@@ -649,10 +649,19 @@ class PGOAgent:
     """
 
     def __init__(self, agent_id: int, d: int, r: int, algorithm: int = QuadraticOptimizer.RTR,
-                 precond: str = "exact"):
+                 precond: str = "exact", acceleration: bool = False, num_robots: int = 1, restart_interval: int = 30):
         self.id, self.d, self.r = agent_id, d, r
         self.algorithm = algorithm
         self.precond = precond
+        self.acceleration = acceleration          # ref include/DPGO/PGOAgent.h:75-79
+        self.num_robots = num_robots
+        self.restart_interval = restart_interval
+        self.gamma = 0.0
+        self.alpha = 0.0
+        self.Y = None
+        self.V = None
+        self.XPrev = None
+        self.neighbor_aux_poses: Dict[Tuple[int, int], np.ndarray] = {}
         self.n = 1
         self.X = None
         self.problem: Optional[QuadraticProblem] = None
@@ -740,12 +749,33 @@ class PGOAgent:
             if pid in wanted:
                 self.neighbor_poses[pid] = val
 
-    def iterate(self, do_optimization: bool = True) -> bool:
-        """ref: src/PGOAgent.cpp:642-718 (non-accelerated branch) + updateX :1093-1165."""
-        self.iteration += 1
+    # -- Nesterov acceleration (ref src/PGOAgent.cpp:1040-1091) ------------------------------------------
+    def initialize_acceleration(self) -> None:
+        self.XPrev = self.X.copy()
+        self.gamma = 0.0
+        self.alpha = 0.0
+        self.V = self.X.copy()
+        self.Y = self.X.copy()
+
+    def get_aux_shared_pose_dict(self):
+        """ref: src/PGOAgent.cpp:107-118."""
+        dh = self.d + 1
+        return {pid: self.Y[:, pid[1] * dh:(pid[1] + 1) * dh].copy() for pid in self.local_shared}
+
+    def update_aux_neighbor_poses(self, neighbor_id: int, pose_dict) -> None:
+        """ref: src/PGOAgent.cpp:460-479."""
+        wanted = set(self.neighbor_shared)
+        for pid, val in pose_dict.items():
+            if pid in wanted:
+                self.neighbor_aux_poses[pid] = val
+
+    def _update_x(self, do_optimization: bool, acceleration: bool) -> bool:
+        """ref: src/PGOAgent.cpp:1093-1165."""
         if not do_optimization:
+            if acceleration:
+                self.X = self.Y.copy()
             return True
-        if not self.construct_G(self.neighbor_poses):
+        if not self.construct_G(self.neighbor_aux_poses if acceleration else self.neighbor_poses):
             return False
         opt = QuadraticOptimizer(self.problem, precond=self.precond)
         opt.algorithm = self.algorithm
@@ -753,9 +783,30 @@ class PGOAgent:
         opt.tr_iterations = 1            # ref :1135
         opt.tr_max_inner = 10            # ref :1136
         opt.tr_initial_radius = 100.0    # ref :1137
-        self.X = opt.optimize(self.X)
+        self.X = opt.optimize(self.Y if acceleration else self.X)
         self.last_result = opt.result
         return True
+
+    def iterate(self, do_optimization: bool = True) -> bool:
+        """ref: src/PGOAgent.cpp:642-718 + updateX :1093-1165."""
+        self.iteration += 1
+        self.XPrev = self.X.copy()
+        if not self.acceleration:
+            return self._update_x(do_optimization, False)
+        N = float(self.num_robots)
+        self.gamma = (1 + math.sqrt(1 + 4 * N * N * self.gamma * self.gamma)) / (2 * N)       # :1065-1069
+        self.alpha = 1.0 / (self.gamma * N)                                                     # :1071-1075
+        self.Y = manifold_project((1 - self.alpha) * self.X + self.alpha * self.V, self.d)      # :1077-1083
+        ok = self._update_x(do_optimization, True)
+        self.V = manifold_project(self.V + self.gamma * (self.X - self.Y), self.d)              # :1085-1091
+        if (self.iteration + 1) % self.restart_interval == 0:                                   # :1033-1038
+            self.X = self.XPrev                                                                 # :1040-1052
+            self._update_x(do_optimization, False)
+            self.V = self.X.copy()
+            self.Y = self.X.copy()
+            self.gamma = 0.0
+            self.alpha = 0.0
+        return ok
 
     def local_pose_graph_optimization(self, T_init: Optional[np.ndarray] = None):
         """ref: src/PGOAgent.cpp:964-990 (r = d problem on private edges, RTR 10/50, tol 0.1)."""
@@ -832,7 +883,8 @@ class MultiRobotDriver:
 
     def __init__(self, meas: Measurements, n: int, k: int, r: int = 5,
                  algorithm: int = QuadraticOptimizer.RTR, precond: str = "exact",
-                 owner: Optional[np.ndarray] = None, T_init: Optional[np.ndarray] = None):
+                 owner: Optional[np.ndarray] = None, T_init: Optional[np.ndarray] = None,
+                 acceleration: bool = False):
         self.meas, self.n, self.k, self.r, self.d = meas, n, k, r, meas.d
         self.owner = contiguous_partition(n, k) if owner is None else owner
         parts, counts, glob = split_measurements(meas, self.owner, k)
@@ -841,7 +893,7 @@ class MultiRobotDriver:
         self.central.set_Q(construct_connection_laplacian(meas, n))
         self.agents = []
         for a in range(k):
-            ag = PGOAgent(a, self.d, r, algorithm=algorithm, precond=precond)
+            ag = PGOAgent(a, self.d, r, algorithm=algorithm, precond=precond, acceleration=acceleration, num_robots=k)
             ag.set_pose_graph(*parts[a], n=int(counts[a]))
             self.agents.append(ag)
         self.T_init = chordal_initialization(meas, n) if T_init is None else T_init     # ref :185
@@ -850,6 +902,8 @@ class MultiRobotDriver:
         for a, ag in enumerate(self.agents):
             cols = (glob[a][:, None] * dh + np.arange(dh)[None, :]).ravel()
             ag.X = self.X_init[:, cols].copy()                                          # ref :188-202
+            if acceleration:
+                ag.initialize_acceleration()                                            # ref setX -> :60-62
         self.selected = 0
         self.trace = RBCDTrace()
 
@@ -870,6 +924,10 @@ class MultiRobotDriver:
         for ag in self.agents:
             if ag.id != sel.id:
                 sel.update_neighbor_poses(ag.id, ag.get_shared_pose_dict())
+        if sel.acceleration:                                               # ref :259-274
+            for ag in self.agents:
+                if ag.id != sel.id:
+                    sel.update_aux_neighbor_poses(ag.id, ag.get_aux_shared_pose_dict())
         sel.iterate(True)
         X = self.assemble()
         RG = self.central.rie_grad(X)
