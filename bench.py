@@ -50,6 +50,15 @@ def measured_peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def ncu_traffic(kernel: str):
+    """DRAM read+write bytes per launch from the committed ncu capture (profiles/traffic.json), else None."""
+    try:
+        t = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))[kernel]
+        return t["dram_bytes_read"] + t["dram_bytes_write"]
+    except Exception:
+        return None
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons DURING the timed region."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
@@ -205,10 +214,11 @@ def spmv_roofline(torch, dp, pg, peak_gbs, peak_src, dims=(100, 100, 40), reps=2
     ms = e0.elapsed_time(e1) / reps
     nbytes = prob.spmv_algorithmic_bytes(False)
     ach = nbytes / (ms * 1e-3) / 1e9
-    res = {"kernel": "k_spmv<5,4> (Out = X Q)", "workload": f"synthetic grid {dims[0]}x{dims[1]}x{dims[2]} = {n} poses, "
+    res = {"kernel": "k_spmv_tma<5,4,192> (Out = X Q; bulk-TMA producer, DMMA consumers)", "workload": f"synthetic grid {dims[0]}x{dims[1]}x{dims[2]} = {n} poses, "
            f"{len(edges)} edges, r={RANK_R}, nb={prob.num_blocks()} blocks", "bound": "hbm", "achieved": ach,
            "peak": peak_gbs, "peak_source": peak_src, "unit": "GB/s", "frac": ach / peak_gbs,
-           "algorithmic_bytes_per_launch": nbytes, "us_per_launch": ms * 1e3, "launches_timed": reps, "traffic": None}
+           "algorithmic_bytes_per_launch": nbytes, "us_per_launch": ms * 1e3, "launches_timed": reps,
+           "traffic": ncu_traffic("k_spmv_tma")}
     prob.close()
     del X, out
     torch.cuda.empty_cache()
@@ -320,7 +330,8 @@ def run_gpu_arm(args):
             "clocks": clocks,
             "roofline": {"kernel": "k_optimize<5,4> (one persistent launch per step)", "bound": "hbm", "achieved": ach,
                          "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": ach / peak,
-                         "algorithmic_bytes_per_launch": alg_bytes, "traffic": None,
+                         "algorithmic_bytes_per_launch": alg_bytes, "traffic": ncu_traffic("k_optimize"),
+                         "traffic_note": "ncu capture of one launch (a 10-tCG step: 11 preconditioner applications)",
                          "note": "bytes = spmv_passes*(132 nb + 4(n+1) + 96 r n) + precond_applies*(8 N^2 + 16 r N), "
                                  "averaged over the cycle; the dense (Q+0.1I)^-1 stream dominates"},
             "trajectory": [{"f": rs.f_opt, "gradnorm": rs.gradnorm_opt, "tcg": rs.tcg_iterations,

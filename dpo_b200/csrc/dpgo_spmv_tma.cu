@@ -142,32 +142,43 @@ __global__ void __launch_bounds__(TMA_THREADS, 2)
     // accumulator fragment leaves Out_j[a, 2k..2k+1] in lane (a,k), k < 2 -- no shuffles, no 128-bit smem
     // broadcasts.  The starting warp rotates with the group so that short groups load all warps evenly.
     const int wrot = (warp + it * 7) % NCONS;
+    const double *Xl = X + off;
+    const double *q_l = q_s + boff;
     for (int j = r0 + wrot; j < r1; j += NCONS) {
       const int lb0 = rp_s[j - r0] - b0, lb1 = rp_s[j - r0 + 1] - b0;
       double c0 = 0.0, c1 = 0.0, e0 = 0.0, e1 = 0.0;      // two accumulator pairs (shorter DMMA chains)
       for (int b = lb0; b < lb1; b += SPMV_BATCH) {
+        const int nrem = lb1 - b;                            // warp-uniform
         double x[SPMV_BATCH];
 #pragma unroll
-        for (int u = 0; u < SPMV_BATCH; u += 2) {          // all global gathers of the batch in flight together
-          if (b + u < lb1) {                                // warp-uniform
-            const int i0 = idx_s[b + u];
-            const bool in1 = (b + u + 1 < lb1);
-            const int i1 = in1 ? idx_s[b + u + 1] : i0;
-            x[u] = valid ? __ldg(X + (size_t)i0 * TS + off) : 0.0;
-            x[u + 1] = (valid && in1) ? __ldg(X + (size_t)i1 * TS + off) : 0.0;
+        for (int u0 = 0; u0 < SPMV_BATCH; u0 += 4) {         // all global gathers of the batch in flight together
+          if (u0 < nrem) {
+#pragma unroll
+            for (int u = u0; u < u0 + 4; ++u) {
+              x[u] = 0.0;
+              if (valid && u < nrem) x[u] = __ldg(Xl + (size_t)idx_s[b + u] * TS);
+            }
           }
         }
 #pragma unroll
-        for (int u = 0; u < SPMV_BATCH; u += 2) {
-          if (b + u < lb1) {
-            const double q0 = bvalid ? q_s[(size_t)(b + u) * 16 + boff] : 0.0;
-            asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
-                         : "+d"(c0), "+d"(c1) : "d"(x[u]), "d"(q0));
-            if (b + u + 1 < lb1) {
-              const double q1 = bvalid ? q_s[(size_t)(b + u + 1) * 16 + boff] : 0.0;
-              asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
-                           : "+d"(e0), "+d"(e1) : "d"(x[u + 1]), "d"(q1));
+        for (int u0 = 0; u0 < SPMV_BATCH; u0 += 4) {
+          if (u0 < nrem) {
+            const double *qb = q_l + (size_t)(b + u0) * 16;
+            double q0 = 0.0, q1 = 0.0, q2 = 0.0, q3 = 0.0;
+            if (bvalid) {
+              q0 = qb[0];
+              if (u0 + 1 < nrem) q1 = qb[16];
+              if (u0 + 2 < nrem) q2 = qb[32];
+              if (u0 + 3 < nrem) q3 = qb[48];
             }
+            asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                         : "+d"(c0), "+d"(c1) : "d"(x[u0]), "d"(q0));
+            asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                         : "+d"(e0), "+d"(e1) : "d"(x[u0 + 1]), "d"(q1));
+            asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                         : "+d"(c0), "+d"(c1) : "d"(x[u0 + 2]), "d"(q2));
+            asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                         : "+d"(e0), "+d"(e1) : "d"(x[u0 + 3]), "d"(q3));
           }
         }
       }

@@ -30,6 +30,22 @@ def raw_page(rep):
     return rows[0], rows[1], rows[2:]
 
 
+def to_bytes(val, unit):
+    mult = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}.get(unit, None)
+    return float(val.replace(",", "")) * mult if mult else None
+
+
+def traffic_of(rep):
+    """DRAM read+write bytes per launch of the (first) kernel in an ncu --set full report."""
+    hdr, units, rows = raw_page(rep)
+    r = rows[0]
+    ir, iw = hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum")
+    return {"kernel": r[hdr.index("Kernel Name")][:80], "dram_bytes_read": to_bytes(r[ir], units[ir]),
+            "dram_bytes_write": to_bytes(r[iw], units[iw]),
+            "duration_us_under_ncu": float(r[hdr.index("gpu__time_duration.sum")].replace(",", "")) *
+            {"us": 1.0, "ms": 1e3, "ns": 1e-3, "s": 1e6}[units[hdr.index("gpu__time_duration.sum")]]}
+
+
 def summarise_rep(rep, path, title, notes):
     hdr, units, rows = raw_page(rep)
     with open(path, "w") as fh:
@@ -85,7 +101,16 @@ def main():
         summarise_rep(sp, os.path.join(OUT, f"{tag}_spmv.md"), "k_spmv_tma — Q.X product on the 400k-pose synthetic grid",
                       "Algorithmic bytes per launch: 604 800 004 (132 nb + 4(n+1) + 64 r n, nb = 3.6 M, n = 400 k, r = 5). "
                       "DRAM read+write should be close to it (no re-reads).")
+    import json
+    traffic = {}
+    if os.path.exists(sp):
+        traffic["k_spmv_tma"] = traffic_of(sp)
     op = os.path.join(g, f"prof_opt_{tag}.ncu-rep")
+    if os.path.exists(op):
+        traffic["k_optimize"] = traffic_of(op)
+    if traffic:
+        with open(os.path.join(OUT, "traffic.json"), "w") as fh:
+            json.dump({"tag": tag, "source": "ncu --set full --clock-control none, one capture per kernel", **traffic}, fh, indent=1)
     if os.path.exists(op):
         summarise_rep(op, os.path.join(OUT, f"{tag}_optimize.md"), "k_optimize — one RTR step on sphere2500 (1 agent, r=5, exact preconditioner)",
                       "One persistent cooperative launch per optimize() call; the dense (Q+0.1I)^-1 stream (800 MB per "
