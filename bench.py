@@ -359,38 +359,58 @@ def run_gpu_arm(args):
             line["cpu_baseline"] = info
         print(json.dumps(line))
     else:
-        run = DistributedPGO(edges, n, world, r=RANK_R, schedule="coloured", X_init=X0, rank=rank, world=world,
-                             device=local_rank, dist=dist)
+        # everything of the multi-GPU rounds (pack, NCCL all-gather, G rebuild, optimise) lives on one side stream so
+        # that a whole cycle of rounds can be captured into a CUDA graph and replayed (launch-bound inner loop)
+        side = torch.cuda.Stream(device=dev)
+        with torch.cuda.stream(side):
+            run = DistributedPGO(edges, n, world, r=RANK_R, schedule="coloured", X_init=X0, rank=rank, world=world,
+                                 device=local_rank, dist=dist)
         ag = run.agents[rank]          # world == number of agents here: one agent per GPU
         dh = d + 1
         cols = (run.glob[rank][:, None] * dh + np.arange(dh)[None, :]).ravel()
         X0d = torch.from_numpy(np.asfortranarray(X0[:, cols]).ravel(order="F").copy()).to(dev)
         rounds_per_cycle = CYCLE * run.ncolours
+        steps_per_cycle = sum(1 for i in range(rounds_per_cycle) if run.colour[rank] == i % run.ncolours)
 
-        def rounds(count):
-            steps = 0
-            for i in range(count):
-                if i % rounds_per_cycle == 0:
-                    ag.mProblem.copy_X_from_device(X0d.data_ptr())
-                    run.round = 0
+        def one_cycle():
+            ag.mProblem.copy_X_from_device(X0d.data_ptr())
+            for i in range(rounds_per_cycle):
                 run.exchange()
-                if run.colour[rank] == run.round % run.ncolours:
+                if run.colour[rank] == i % run.ncolours:
                     ag.opt.optimize_resident_async()
-                    steps += 1
-                run.round += 1
-            return steps
 
-        rounds(max(W, run.ncolours))
+        ncycles = max(1, K // rounds_per_cycle)
+        K = ncycles * rounds_per_cycle             # timed rounds: whole cycles
+        # (capturing a cycle -- cooperative kernels + NCCL all-gathers -- into one CUDA graph was tried and hangs at
+        #  replay on this stack, so the rounds are launched eagerly from the host)
+        graph, graph_note = None, "eager launches"
+        with torch.cuda.stream(side):
+            for _ in range(max(2, (W + rounds_per_cycle - 1) // rounds_per_cycle)):
+                one_cycle()
+        barrier()
+
+        def run_cycles(count):
+            with torch.cuda.stream(side):
+                for _ in range(count):
+                    if graph is not None:
+                        graph.replay()
+                    else:
+                        one_cycle()
+
+        run_cycles(2)
         barrier()
         sampler = ClockSampler(local_rank)
         if rank == 0:
             sampler.start()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         barrier()
-        e0.record()
-        my_steps = rounds(K)
-        e1.record()
+        with torch.cuda.stream(side):
+            e0.record()
+        run_cycles(ncycles)
+        with torch.cuda.stream(side):
+            e1.record()
         barrier()
+        my_steps = ncycles * steps_per_cycle
         t = torch.tensor([e0.elapsed_time(e1), float(my_steps)], dtype=torch.float64, device=dev)
         tmax = t.clone()
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
@@ -398,25 +418,29 @@ def run_gpu_arm(args):
         dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
         ms_total = float(tmax[0])
         total_steps = float(tsum[1])
-        st = run.step(evaluate=True)
+        line["steps"] = K
+        with torch.cuda.stream(side):
+            st = run.step(evaluate=True)
         # ---- end to end: the same coloured rounds driven through the host-level API (host matrices in and out,
         #      public poses packed on the host, H2D / all-gather / D2H inside the timed region) ----
         ag.mProblem.sync()
         ag.X = np.array(X0[:, cols])
         run.round = 0
         KE = max(4, K // 4)
-        for _ in range(2 * run.ncolours):
-            run.step_host()
+        with torch.cuda.stream(side):
+            for _ in range(2 * run.ncolours):
+                run.step_host()
         barrier()
         t0 = time.perf_counter()
         host_steps = 0
-        for i in range(KE):
-            if i % rounds_per_cycle == 0:
-                ag.X = np.array(X0[:, cols])
-                run.round = 0
-            if run.colour[rank] == run.round % run.ncolours:
-                host_steps += 1
-            run.step_host()
+        with torch.cuda.stream(side):
+            for i in range(KE):
+                if i % rounds_per_cycle == 0:
+                    ag.X = np.array(X0[:, cols])
+                    run.round = 0
+                if run.colour[rank] == run.round % run.ncolours:
+                    host_steps += 1
+                run.step_host()
         barrier()
         e2e_dt = time.perf_counter() - t0
         te = torch.tensor([e2e_dt, float(host_steps)], dtype=torch.float64, device=dev)
@@ -430,7 +454,7 @@ def run_gpu_arm(args):
             line.update({
                 "value": total_steps / (ms_total * 1e-3), "ms_per_step": ms_total / K,
                 "config": dict(workload_config(world, f"coloured RBCD ({run.ncolours} colours), one agent per GPU"),
-                               rounds=K, agent_steps=int(total_steps),
+                               rounds=K, agent_steps=int(total_steps), launch_mode=graph_note,
                                allgather_bytes_per_rank=pub_bytes, parallelism=f"agents{world}"),
                 "rounds_per_sec": K / (ms_total * 1e-3),
                 "e2e": {"value": float(te_sum[1]) / float(te_max[0]), "unit": UNIT, "h2d_bytes_per_step": h2d,
