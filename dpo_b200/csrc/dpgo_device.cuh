@@ -7,12 +7,13 @@
 //     bval[b*16 + k*4 + c] = Q[(d+1)i + k, (d+1)j + c] for the block b of output tile j whose
 //     neighbour tile is i = bcol[b]  (so Out_j[a,c] = sum_b sum_k P_i[a,k] * bval[b][k][c]).
 //
-// Lane mapping ("element per lane"): a sub-group of SG lanes owns one pose tile; lane l holds
-// element (a = l>>2, c = l&3) of every vector's tile, valid iff a < R and c < DH.  The same
-// mapping is the (a,k) operand position of the gather: lane (a,k) loads P_i[a,k] once (the
+// Lane mapping ("element per lane") of the persistent kernel: a sub-group of SG lanes owns one pose
+// tile; lane l holds element (a = l>>2, c = l&3) of every vector's tile, valid iff a < R and c < DH.
+// The same mapping is the (a,k) operand position of the gather: lane (a,k) loads P_i[a,k] once (the
 // sub-group covers the neighbour tile exactly once, coalesced) and row k of the 4x4 block
 // (2 x 128-bit loads, broadcast across a), accumulates 4 partial outputs, and a reduce-scatter
-// over k (warp shuffles) leaves Out_j[a,c] in lane (a,c).
+// over k (warp shuffles) leaves Out_j[a,c] in lane (a,c).  (The stand-alone SpMV in
+// dpgo_spmv_tma.cu feeds the same operands to the fp64 tensor pipe instead.)
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>

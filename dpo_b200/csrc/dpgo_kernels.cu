@@ -998,12 +998,6 @@ cudaError_t launch_pack_tiles(int ts, int count, const int *pose, const double *
 }
 
 
-__global__ void k_scatter_dense(const int *__restrict__ row, const int *__restrict__ col, const double *__restrict__ val,
-                                int64_t count, double *__restrict__ A, int N) {
-  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (t < count) A[(size_t)row[t] + (size_t)N * col[t]] = val[t];
-}
-
 // dense A <- block-CSR Q (+ shift * I): one thread per (block, entry); the output tile of block b is found by
 // binary search in rowptr.  A[(dh*i + k) + N*(dh*j + c)] = bval[b][k][c] with i = bcol[b], j = row of b.
 __global__ void k_bsr_to_dense(int n, int dh, int64_t nb, const int *__restrict__ rowptr, const int *__restrict__ bcol,
@@ -1030,13 +1024,6 @@ cudaError_t launch_bsr_to_dense(int n, int dh, int64_t nb, const int *rowptr, co
                                 double shift, double *A, int N, cudaStream_t stream) {
   if (nb > 0) k_bsr_to_dense<<<(unsigned)((nb * 16 + 255) / 256), 256, 0, stream>>>(n, dh, nb, rowptr, bcol, bval, A, N);
   k_add_diag<<<(N + 255) / 256, 256, 0, stream>>>(A, N, shift);
-  return cudaGetLastError();
-}
-
-cudaError_t launch_scatter_dense(const int *row, const int *col, const double *val, int64_t count, double *A, int N,
-                                 cudaStream_t stream) {
-  if (count <= 0) return cudaSuccess;
-  k_scatter_dense<<<(unsigned)((count + 255) / 256), 256, 0, stream>>>(row, col, val, count, A, N);
   return cudaGetLastError();
 }
 

@@ -15,7 +15,7 @@ enum VecId {
   V_ETA, V_RES, V_Z,     // tCG: step, residual, preconditioned residual
   V_D0, V_D1,            // tCG: search direction double buffer
   V_HD,                  // H[delta]
-  V_T,                   // dense-preconditioner scratch
+  V_T,                   // scratch (Stiefel projection output)
   V_XIN,                 // copy of the input iterate (relative change)
   V_AUX,                 // operand of the single-operation entry points
   V_COUNT
@@ -73,8 +73,6 @@ cudaError_t launch_build_G(int r, int dh, int nposes, const int *pose_ids, const
                            double *G, cudaStream_t stream);
 cudaError_t launch_bsr_to_dense(int n, int dh, int64_t nb, const int *rowptr, const int *bcol, const double *bval,
                                 double shift, double *A, int N, cudaStream_t stream);
-cudaError_t launch_scatter_dense(const int *row, const int *col, const double *val, int64_t count, double *A, int N,
-                                 cudaStream_t stream);
 
 // dense SPD inverse in place (dense_inverse.cu); A is N x N, ld = N, symmetric positive definite
 cudaError_t dense_spd_inverse(double *A, int N, cudaStream_t stream);

@@ -22,8 +22,8 @@ struct Triplet {
 
 class SparseLDL {
  public:
-  // entries of the FULL symmetric matrix (both triangles or either one; duplicates are summed; (r,c) and
-  // (c,r) entries are merged into the upper triangle)
+  // entries: ONE triangle of the symmetric matrix (each off-diagonal pair given once, as (r,c) or (c,r));
+  // duplicates of the same position are summed
   void factor(int n, const std::vector<Triplet> &entries) {
     n_ = n;
     // --- adjacency for the ordering
@@ -40,16 +40,16 @@ class SparseLDL {
     for (const Triplet &t : entries) {
       int i = inv_[(size_t)t.r], j = inv_[(size_t)t.c];
       if (i > j) std::swap(i, j);
-      up.push_back({i, j, (t.r == t.c) ? t.v : t.v});
+      up.push_back({i, j, t.v});
     }
-    // symmetric input given with both triangles would double the off-diagonals: detect by halving when both present
     std::sort(up.begin(), up.end(), [](const Triplet &a, const Triplet &b) { return a.c != b.c ? a.c < b.c : a.r < b.r; });
     Ap_.assign((size_t)n + 1, 0);
     Ai_.clear();
     Ax_.clear();
+    int cur_col = -1;
     for (size_t q = 0; q < up.size(); ++q) {
-      if (!Ai_.empty() && Ap_cur_ == up[q].c && Ai_.back() == up[q].r) Ax_.back() += up[q].v;
-      else { Ai_.push_back(up[q].r); Ax_.push_back(up[q].v); Ap_[(size_t)up[q].c + 1]++; Ap_cur_ = up[q].c; }
+      if (!Ai_.empty() && cur_col == up[q].c && Ai_.back() == up[q].r) Ax_.back() += up[q].v;
+      else { Ai_.push_back(up[q].r); Ax_.push_back(up[q].v); Ap_[(size_t)up[q].c + 1]++; cur_col = up[q].c; }
     }
     for (int k = 0; k < n; ++k) Ap_[(size_t)k + 1] += Ap_[(size_t)k];
     symbolic();
@@ -75,7 +75,7 @@ class SparseLDL {
   size_t nnzL() const { return Li_.size(); }
 
  private:
-  int n_ = 0, Ap_cur_ = -1;
+  int n_ = 0;
   std::vector<int> perm_, inv_, Ap_, Ai_, Lp_, Li_, parent_, lnz_;
   std::vector<double> Ax_, Lx_, D_;
 
