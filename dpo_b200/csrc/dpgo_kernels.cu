@@ -340,6 +340,9 @@ template <int R> __device__ void phase_dense_tma(const KParams &kp, const double
     if (warp == (OPT_THREADS / 32 - 1)) {
       // ---------------- producer ----------------
       if (lane == 0) {
+        // evict-first: the 8 N^2 byte stream must not push the partial products / work vectors out of L2
+        uint64_t pol;
+        asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
         unsigned c = ring.count;
         for (int sg = 0; sg < nseg; ++sg) {
           const int c0 = sg * DENSE_SEG;
@@ -349,9 +352,9 @@ template <int R> __device__ void phase_dense_tma(const KParams &kp, const double
             if (c >= DENSE_NST) mbar_wait_parity(&ring.empty[st], ((c / DENSE_NST) - 1) & 1);
             asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(&ring.full[st])), "r"(bytes)
                          : "memory");
-            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(
                              smem_addr(ring.buf + (size_t)st * DENSE_SEG)),
-                         "l"(kp.pinv + (size_t)(k0 + kk) * N + c0), "r"(bytes), "r"(smem_addr(&ring.full[st]))
+                         "l"(kp.pinv + (size_t)(k0 + kk) * N + c0), "r"(bytes), "r"(smem_addr(&ring.full[st])), "l"(pol)
                          : "memory");
           }
         }
