@@ -53,8 +53,10 @@ struct dpgo_problem {
   int *d_rowptr = nullptr, *d_bcol = nullptr, *d_cta_rows = nullptr;
   int2 *d_groups = nullptr;      // row groups of the TMA-fed SpMV
   int ngroups = 0;
-  double *d_bval = nullptr, *d_dinv = nullptr, *d_pinv = nullptr, *d_dense_part = nullptr;
+  double *d_bval = nullptr, *d_dinv = nullptr, *d_pinv = nullptr, *d_dense_part = nullptr, *d_dense_t2 = nullptr;
   int dense_per = 1;
+  int sym_ok = 0;                // symmetric (upper-triangle) dense preconditioner planned
+  int *d_sym_ptr = nullptr, *d_sym_g0 = nullptr;
   // vectors
   double *d_G = nullptr;
   double *d_vec[dpgo::V_COUNT] = {};
@@ -89,6 +91,10 @@ void fill_kparams(const dpgo_problem *p, dpgo::KParams &kp, int op, const dpgo_o
   kp.pinv = p->d_pinv;
   kp.dense_part = p->d_dense_part;
   kp.dense_per = p->dense_per;
+  kp.sym_ok = p->sym_ok;
+  kp.sym_ptr = p->d_sym_ptr;
+  kp.sym_g0 = p->d_sym_g0;
+  kp.dense_t2 = p->d_dense_t2;
   kp.cta_rows = p->d_cta_rows;
   kp.G = p->d_G;
   for (int i = 0; i < dpgo::V_COUNT; ++i) kp.v[i] = p->d_vec[i];
@@ -131,6 +137,43 @@ int ensure_dense(dpgo_problem *p) {
     free_dev(p->d_pinv);
     free_dev(p->d_dense_part);
     return fail(DPGO_ERR_CUDA, std::string("dense preconditioner setup: ") + cudaGetErrorString(e));
+  }
+  // Plan of the symmetric (upper-triangle) variant: rows in groups of 8, group g streams columns >= 8g only.
+  // Group b goes to CTA b first (so CTA b's panel starts at column 8b -- phase_pz relies on it), the remaining
+  // groups by decreasing trapezoid area to the least-loaded CTA (LPT).  Used for even N >= 2048 when no CTA gets
+  // more than 16 groups and the imbalance stays small; otherwise the full-matrix stream is used.
+  static const bool no_sym = [] { const char *e2 = std::getenv("DPGO_DENSE_FULL"); return e2 && e2[0] == '1'; }();
+  p->sym_ok = 0;
+  if (!no_sym && (N % 2 == 0) && N >= 2048) {
+    const int G = p->grid, NG = (int)((N + 7) / 8);
+    std::vector<std::vector<int>> lists((size_t)G);
+    std::vector<double> load((size_t)G, 0.0);
+    for (int g = 0; g < NG; ++g) {
+      int best = 0;
+      if (g < G) best = g;
+      else
+        for (int b = 1; b < G; ++b)
+          if (load[(size_t)b] < load[(size_t)best]) best = b;
+      lists[(size_t)best].push_back(8 * g);
+      load[(size_t)best] += (double)((int)N - 8 * g);
+    }
+    size_t maxg = 0;
+    double lmax = 0, lsum = 0;
+    for (int b = 0; b < G; ++b) { maxg = std::max(maxg, lists[(size_t)b].size()); lmax = std::max(lmax, load[(size_t)b]); lsum += load[(size_t)b]; }
+    if (maxg <= 16 && lmax <= 1.15 * lsum / G) {
+      std::vector<int> ptr((size_t)G + 1, 0), g0s;
+      for (int b = 0; b < G; ++b) {
+        std::sort(lists[(size_t)b].begin(), lists[(size_t)b].end());
+        g0s.insert(g0s.end(), lists[(size_t)b].begin(), lists[(size_t)b].end());
+        ptr[(size_t)b + 1] = (int)g0s.size();
+      }
+      DPGO_CUDA(cudaMalloc(&p->d_sym_ptr, sizeof(int) * ptr.size()));
+      DPGO_CUDA(cudaMalloc(&p->d_sym_g0, sizeof(int) * std::max<size_t>(g0s.size(), 1)));
+      DPGO_CUDA(cudaMalloc(&p->d_dense_t2, sizeof(double) * (size_t)p->r * N));
+      DPGO_CUDA(cudaMemcpy(p->d_sym_ptr, ptr.data(), sizeof(int) * ptr.size(), cudaMemcpyHostToDevice));
+      DPGO_CUDA(cudaMemcpy(p->d_sym_g0, g0s.data(), sizeof(int) * g0s.size(), cudaMemcpyHostToDevice));
+      p->sym_ok = 1;
+    }
   }
   return DPGO_OK;
 }
@@ -240,6 +283,8 @@ int build_from_triplets(dpgo_problem *p, std::vector<BlockTriplet> &trip, unsign
   cudaSetDevice(p->device);
   free_dev(p->d_rowptr); free_dev(p->d_bcol); free_dev(p->d_bval); free_dev(p->d_dinv); free_dev(p->d_pinv);
   free_dev(p->d_cta_rows); free_dev(p->d_partials); free_dev(p->d_dense_part); free_dev(p->d_groups);
+  free_dev(p->d_dense_t2); free_dev(p->d_sym_ptr); free_dev(p->d_sym_g0);
+  p->sym_ok = 0;
   p->have_Q = false;
   p->ngroups = 0;
   // +8 ints of slack: the bulk-TMA windows are rounded out to 16 bytes
@@ -405,6 +450,7 @@ int dpgo_problem_destroy(dpgo_problem_t *p) {
   if (p->stream) cudaStreamSynchronize(p->stream);
   free_dev(p->d_rowptr); free_dev(p->d_bcol); free_dev(p->d_cta_rows); free_dev(p->d_bval); free_dev(p->d_groups);
   free_dev(p->d_dinv); free_dev(p->d_pinv); free_dev(p->d_dense_part); free_dev(p->d_G);
+  free_dev(p->d_dense_t2); free_dev(p->d_sym_ptr); free_dev(p->d_sym_g0);
   for (int i = 0; i < dpgo::V_COUNT; ++i) free_dev(p->d_vec[i]);
   free_dev(p->d_S[0]); free_dev(p->d_S[1]); free_dev(p->d_partials); free_dev(p->d_bar); free_dev(p->d_result);
   free_dev(p->d_public); free_dev(p->d_pose_ids); free_dev(p->d_pose_ptr); free_dev(p->d_edge_slot);

@@ -301,6 +301,8 @@ template <int R> __device__ void phase_dense(const KParams &kp, const double *V,
 constexpr int DENSE_NST = 6;
 constexpr int DENSE_CONS = OPT_THREADS - 32;          // 480 consumer threads
 constexpr int DENSE_SEG = DENSE_CONS * 4;             // 1920 columns per chunk
+constexpr int DENSE_RING_DOUBLES = 3 * 8 * ((OPT_THREADS / 32 - 1) * 32 + 4);   // max(6 x 1920, 3 x 8 x 484) doubles
+static_assert(DENSE_RING_DOUBLES >= DENSE_NST * DENSE_SEG, "ring must hold the full-matrix stages too");
 
 struct DenseRing {
   double *buf;          // DENSE_NST * DENSE_SEG doubles
@@ -400,11 +402,159 @@ template <int R> __device__ void phase_dense_tma(const KParams &kp, const double
   ring.count += total;
 }
 
+// ---- symmetric variant: read only the upper triangle of Pinv --------------------------------------------------
+// T = V * Pinv with Pinv symmetric.  The rows are cut into groups of 8; a group g (rows g0..g0+7) streams only the
+// columns c >= g0 of its rows (upper trapezoid: half the bytes).  Every 8x8 tile right of the diagonal feeds TWO
+// products from shared memory:
+//   direct      T[:, ctile..] += V[:, g0..]   * P[g0.., ctile..]      (accumulated per column, over the CTA's groups)
+//   transposed  T[:, g0..]    += V[:, ctile..] * P[g0.., ctile..]^T    (accumulated per row group)
+// and the diagonal tile feeds the direct product only.  Both are mma.sync m8n8k4 (DMMA): the 8x8 tile is read from
+// shared memory in the two B-fragment layouts, so the k-reduction of the transposed product happens inside the tensor
+// op -- no cross-lane reduction per element.  Groups are dealt to CTAs by decreasing trapezoid area (LPT, host side,
+// <1-5 % imbalance); per CTA the direct partials form one panel (as in the full variant), the transposed results
+// are complete per row group after a fixed-order sum over the 15 consumer warps.  Same producer/consumer ring.
+constexpr int SYM_NST = 3;
+constexpr int SYM_SEG = (OPT_THREADS / 32 - 1) * 32;   // 480 columns per segment: 32 per consumer warp
+constexpr int SYM_SROW = SYM_SEG + 4;                   // staged row pitch: 3872 B = 32 mod 128 (conflict-light tile reads)
+constexpr int SYM_STAGE = 8 * SYM_SROW;                 // doubles per stage (8 rows)
+constexpr int SYM_MAXG = 16;                            // row groups per CTA (host falls back beyond)
+
+__device__ __forceinline__ void dmma884(double &d0, double &d1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
+}
+
+template <int R> __device__ void phase_dense_sym(const KParams &kp, const double *V, double *sV, DenseRing &ring, double *sAcc2) {
+  const int N = kp.N;
+  const int nseg = (N + SYM_SEG - 1) / SYM_SEG;
+  const int gp0 = ld_const(kp.sym_ptr + blockIdx.x), ng = ld_const(kp.sym_ptr + blockIdx.x + 1) - gp0;
+  const int *glist = kp.sym_g0 + gp0;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  constexpr int NCW = OPT_THREADS / 32 - 1;             // consumer warps
+  // V rows of my groups (direct-product A operands) and the transposed accumulators
+  for (int q = threadIdx.x; q < ng * 8 * R; q += blockDim.x) {
+    const int gi = q / (8 * R), rem = q - gi * 8 * R, rr = rem / R, a = rem - rr * R;
+    const int row = ld_const(glist + gi) + rr;
+    sV[q] = (row < N) ? __ldcg(V + (size_t)row * R + a) : 0.0;
+  }
+  for (int q = threadIdx.x; q < NCW * ng * 8 * R; q += blockDim.x) sAcc2[q] = 0.0;
+  __syncthreads();
+  unsigned total = 0;
+  for (int sg = 0; sg < nseg; ++sg) {
+    const int s1 = min(N, (sg + 1) * SYM_SEG);
+    for (int gi = 0; gi < ng; ++gi) total += (ld_const(glist + gi) < s1) ? 1u : 0u;
+  }
+  if (warp == NCW) {
+    // ---------------- producer ----------------
+    if (lane == 0) {
+      uint64_t pol;
+      asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+      unsigned c = ring.count;
+      for (int sg = 0; sg < nseg; ++sg) {
+        const int s0 = sg * SYM_SEG, s1 = min(N, s0 + SYM_SEG);
+        for (int gi = 0; gi < ng; ++gi) {
+          const int g0 = ld_const(glist + gi);
+          if (g0 >= s1) continue;
+          const int col_lo = max(s0, g0);
+          const unsigned rowbytes = (unsigned)(s1 - col_lo) * 8u;
+          const int nrows = min(8, N - g0);
+          const int st = c % SYM_NST;
+          if (c >= SYM_NST) mbar_wait_parity(&ring.empty[st], ((c / SYM_NST) - 1) & 1);
+          asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(&ring.full[st])),
+                       "r"(rowbytes * (unsigned)nrows)
+                       : "memory");
+          for (int rr = 0; rr < nrows; ++rr)
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(
+                             smem_addr(ring.buf + (size_t)st * SYM_STAGE + (size_t)rr * SYM_SROW)),
+                         "l"(kp.pinv + (size_t)(g0 + rr) * N + col_lo), "r"(rowbytes), "r"(smem_addr(&ring.full[st])), "l"(pol)
+                         : "memory");
+          ++c;
+        }
+      }
+    }
+  } else {
+    // ---------------- consumers ----------------
+    const int a = lane >> 2, k = lane & 3;                // A fragment: row a, column k ; D fragment: row a, columns 2k, 2k+1
+    const int bn = lane >> 2, bk = lane & 3;              // B fragment: column n = lane>>2, row k = lane&3
+    const int gmin = (ng > 0) ? ld_const(glist) : N;
+    double *part = kp.dense_part + (size_t)blockIdx.x * R * N;
+    unsigned c = ring.count;
+    for (int sg = 0; sg < nseg; ++sg) {
+      const int s0 = sg * SYM_SEG, s1 = min(N, s0 + SYM_SEG);
+      const int cw0 = s0 + 32 * warp;
+      double va[4][2];                                    // transposed-product A operands: V[a, ctile + 4q + k]
+#pragma unroll
+      for (int t = 0; t < 4; ++t)
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+          const int col = cw0 + 8 * t + 4 * q + k;
+          va[t][q] = (a < R && col < N) ? __ldcg(V + (size_t)col * R + a) : 0.0;
+        }
+      double D1[4][2];
+#pragma unroll
+      for (int t = 0; t < 4; ++t) D1[t][0] = D1[t][1] = 0.0;
+      for (int gi = 0; gi < ng; ++gi) {
+        const int g0 = ld_const(glist + gi);
+        if (g0 >= s1) continue;
+        const int col_lo = max(s0, g0);
+        const int st = c % SYM_NST;
+        mbar_wait_parity(&ring.full[st], (c / SYM_NST) & 1);
+        const double *base = ring.buf + (size_t)st * SYM_STAGE;
+        const double a1_0 = (a < R) ? sV[(gi * 8 + k) * R + a] : 0.0;          // V[a, g0 + k]
+        const double a1_1 = (a < R) ? sV[(gi * 8 + 4 + k) * R + a] : 0.0;      // V[a, g0 + 4 + k]
+        double D2_0 = 0.0, D2_1 = 0.0;
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+          const int ctile = cw0 + 8 * t;
+          if (ctile < g0 || ctile >= s1) continue;         // warp-uniform: left of the diagonal / past the segment
+          const int x = ctile - col_lo;
+          // direct: B[kk][n] = P[g0 + 4q + kk][ctile + n]
+          dmma884(D1[t][0], D1[t][1], a1_0, base[(size_t)bk * SYM_SROW + x + bn]);
+          dmma884(D1[t][0], D1[t][1], a1_1, base[(size_t)(4 + bk) * SYM_SROW + x + bn]);
+          if (ctile > g0) {
+            // transposed: B[c'][n] = P[g0 + n][ctile + 4q + c']
+            dmma884(D2_0, D2_1, va[t][0], base[(size_t)bn * SYM_SROW + x + bk]);
+            dmma884(D2_0, D2_1, va[t][1], base[(size_t)bn * SYM_SROW + x + 4 + bk]);
+          }
+        }
+        if (a < R) {                                        // rows g0 + 2k, g0 + 2k + 1 of the transposed result
+          double *acc2 = sAcc2 + ((size_t)(warp * ng + gi) * 8 + 2 * k) * R + a;
+          acc2[0] += D2_0;
+          acc2[R] += D2_1;
+        }
+        __syncwarp();
+        if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_addr(&ring.empty[st])) : "memory");
+        ++c;
+      }
+      if (a < R) {
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+          const int col = cw0 + 8 * t + 2 * k;
+          if (col >= gmin && col < N) part[(size_t)col * R + a] = D1[t][0];
+          if (col + 1 >= gmin && col + 1 < N) part[(size_t)(col + 1) * R + a] = D1[t][1];
+        }
+      }
+    }
+  }
+  ring.count += total;
+  __syncthreads();
+  // transposed results: fixed-order sum over the consumer warps
+  for (int q = threadIdx.x; q < ng * 8 * R; q += blockDim.x) {
+    const int gi = q / (8 * R), rem = q - gi * 8 * R, rr = rem / R, a = rem - rr * R;
+    const int row = ld_const(glist + gi) + rr;
+    if (row < N) {
+      double sum = 0.0;
+      for (int w = 0; w < NCW; ++w) sum += sAcc2[((size_t)(w * ng + gi) * 8 + rr) * R + a];
+      kp.dense_t2[(size_t)row * R + a] = sum;
+    }
+  }
+}
+
 template <int R, int DH>
 __device__ void phase_pz(const KParams &kp, int cb, const double *V, double *Zout, double (&acc)[NRED]) {
   constexpr int TS = R * DH;
   const double *X = kp.v[V_X0 + cb];
-  const int nslabs = (kp.N + kp.dense_per - 1) / kp.dense_per;
+  const bool symm = kp.sym_ok != 0;
+  const int nslabs_full = (kp.N + kp.dense_per - 1) / kp.dense_per;
   const size_t stride = (size_t)R * kp.N;
   RowIter<R> it(kp);
   const bool valid = (it.a < R) && (it.c < DH);
@@ -419,6 +569,11 @@ __device__ void phase_pz(const KParams &kp, int cb, const double *V, double *Zou
     double t = 0.0;
     if (ld) {
       const double *pp = kp.dense_part + idx;
+      // symmetric variant: column col = js*DH + c receives direct partials from the CTAs whose first row group
+      // starts at or before it (the host deals group b to CTA b first, so these are CTAs 0 .. col/8), plus the
+      // transposed result of its own row
+      const int nslabs = symm ? min(kp.grid, (js * DH + it.c) / 8 + 1) : nslabs_full;
+      if (symm) t = __ldcg(kp.dense_t2 + idx);
       int b = 0;
       // fixed summation order (slab 0, 1, 2, ...) with 16 independent L2 loads in flight per lane
       for (; b + 16 <= nslabs; b += 16) {
@@ -528,12 +683,17 @@ template <int R, int DH> __global__ void __launch_bounds__(OPT_THREADS, 1) k_opt
   double *sV = bc.sm_out + NRED;                // dense-preconditioner staging (dense_per * R doubles)
   DenseRing ring;
   ring.buf = sV + (size_t)DENSE_PER_MAX * R;    // 16-byte aligned: every preceding block is a multiple of 2 doubles
-  ring.full = reinterpret_cast<uint64_t *>(ring.buf + (size_t)DENSE_NST * DENSE_SEG);
+  ring.full = reinterpret_cast<uint64_t *>(ring.buf + (size_t)DENSE_RING_DOUBLES);
   ring.empty = ring.full + DENSE_NST;
   ring.count = 0;
+  double *sAcc2 = reinterpret_cast<double *>(ring.empty + DENSE_NST);   // symmetric variant: 15 x SYM_MAXG x 8 x R
   // bulk-TMA streaming needs 16-byte aligned rows (N even) and only pays off for a real stream
   const bool dense_tma = (kp.pinv != nullptr) && ((kp.N & 1) == 0) && (kp.N >= 2048);
+  const bool dense_sym = dense_tma && (kp.sym_ok != 0);
   if (dense_tma) {
+    if (dense_sym) {       // stale shared memory must be finite: tiles past N are multiplied by zero operands
+      for (int q = threadIdx.x; q < DENSE_RING_DOUBLES; q += blockDim.x) ring.buf[q] = 0.0;
+    }
     if (threadIdx.x == 0) {
       for (int st = 0; st < DENSE_NST; ++st) {
         asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(&ring.full[st])), "r"(1));
@@ -564,7 +724,9 @@ template <int R, int DH> __global__ void __launch_bounds__(OPT_THREADS, 1) k_opt
   }
   if (kp.op == OP_PRECON) {
     if (precond == DPGO_PRECOND_DENSE_EXACT) {
-      if (dense_tma) phase_dense_tma<R>(kp, kp.v[V_AUX], sV, ring); else phase_dense<R>(kp, kp.v[V_AUX], sV);
+      if (dense_sym) phase_dense_sym<R>(kp, kp.v[V_AUX], sV, ring, sAcc2);
+      else if (dense_tma) phase_dense_tma<R>(kp, kp.v[V_AUX], sV, ring);
+      else phase_dense<R>(kp, kp.v[V_AUX], sV);
       zero(acc); phase_end<0>(kp, bc, acc);
       zero(acc); phase_pz<R, DH>(kp, 0, kp.v[V_AUX], kp.v[V_Z], acc);
       phase_end<1>(kp, bc, acc);
@@ -653,7 +815,9 @@ template <int R, int DH> __global__ void __launch_bounds__(OPT_THREADS, 1) k_opt
     while (true) {
       // -- z0 = M^-1 g for the dense preconditioner (pose-local ones were fused into phase E)
       if (!z0_valid) {
-        if (dense_tma) phase_dense_tma<R>(kp, kp.v[V_RG0 + cb], sV, ring); else phase_dense<R>(kp, kp.v[V_RG0 + cb], sV);
+        if (dense_sym) phase_dense_sym<R>(kp, kp.v[V_RG0 + cb], sV, ring, sAcc2);
+        else if (dense_tma) phase_dense_tma<R>(kp, kp.v[V_RG0 + cb], sV, ring);
+        else phase_dense<R>(kp, kp.v[V_RG0 + cb], sV);
         zero(acc); phase_end<0>(kp, bc, acc);
         zero(acc); phase_pz<R, DH>(kp, cb, kp.v[V_RG0 + cb], kp.v[V_Z00 + cb], acc);
         phase_end<1>(kp, bc, acc);
@@ -700,7 +864,9 @@ template <int R, int DH> __global__ void __launch_bounds__(OPT_THREADS, 1) k_opt
         }
         double zr_new = acc[1];
         if (precond == DPGO_PRECOND_DENSE_EXACT) {
-          if (dense_tma) phase_dense_tma<R>(kp, kp.v[V_RES], sV, ring); else phase_dense<R>(kp, kp.v[V_RES], sV);
+          if (dense_sym) phase_dense_sym<R>(kp, kp.v[V_RES], sV, ring, sAcc2);
+          else if (dense_tma) phase_dense_tma<R>(kp, kp.v[V_RES], sV, ring);
+          else phase_dense<R>(kp, kp.v[V_RES], sV);
           zero(acc); phase_end<0>(kp, bc, acc);
           zero(acc); phase_pz<R, DH>(kp, cb, kp.v[V_RES], kp.v[V_Z], acc);
           phase_end<1>(kp, bc, acc);
@@ -916,7 +1082,7 @@ __global__ void k_build_G(int nposes, const int *__restrict__ pose_ids, const in
 // launchers
 // ---------------------------------------------------------------------------------------------
 template <int R, int DH> static cudaError_t launch_optimize_t(const KParams &kp, cudaStream_t stream) {
-  const size_t smem = ((OPT_THREADS / 32) * NRED + NRED + (size_t)DENSE_PER_MAX * R + (size_t)DENSE_NST * DENSE_SEG + 2 * DENSE_NST) * sizeof(double);
+  const size_t smem = ((OPT_THREADS / 32) * NRED + NRED + (size_t)DENSE_PER_MAX * R + (size_t)DENSE_RING_DOUBLES + 2 * DENSE_NST + (size_t)(OPT_THREADS / 32 - 1) * 16 * 8 * R) * sizeof(double);
   static bool attr_set[64] = {};
   int dev = 0;
   cudaGetDevice(&dev);
@@ -930,7 +1096,7 @@ template <int R, int DH> static cudaError_t launch_optimize_t(const KParams &kp,
 }
 
 template <int R, int DH> static int max_grid_t(int device) {
-  const size_t smem = ((OPT_THREADS / 32) * NRED + NRED + (size_t)DENSE_PER_MAX * R + (size_t)DENSE_NST * DENSE_SEG + 2 * DENSE_NST) * sizeof(double);
+  const size_t smem = ((OPT_THREADS / 32) * NRED + NRED + (size_t)DENSE_PER_MAX * R + (size_t)DENSE_RING_DOUBLES + 2 * DENSE_NST + (size_t)(OPT_THREADS / 32 - 1) * 16 * 8 * R) * sizeof(double);
   cudaFuncSetAttribute(k_optimize<R, DH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   int per_sm = 0, sms = 0;
   if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_optimize<R, DH>, OPT_THREADS, smem) != cudaSuccess) return 0;

@@ -47,6 +47,10 @@ struct KParams {
   const double *pinv;    // N*N    dense inverse of Q+0.1I, may be null
   double *dense_part;    // grid * r * N  per-CTA partial products of the dense preconditioner
   int dense_per;         // rows of pinv per CTA
+  int sym_ok;            // symmetric (upper-triangle) variant of the dense preconditioner is planned
+  const int *sym_ptr;    // grid+1: per-CTA range into sym_g0
+  const int *sym_g0;     // first row of each 8-row group, per CTA ascending
+  double *dense_t2;      // r x N transposed-product results
   const int *cta_rows;   // grid+1 balanced row partition
   const double *G;       // linear term r x N
   double *v[V_COUNT];
