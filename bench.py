@@ -314,10 +314,15 @@ def run_gpu_arm(args):
         # ---- roofline of the dominant kernel of the step: the persistent k_optimize launch ----
         spmv_b = prob.spmv_algorithmic_bytes(True)
         N = (d + 1) * n
-        per_step = []
+        pre_b = prob.precond_algorithmic_bytes(dp.PRECOND_DENSE_EXACT)      # unique bytes (upper triangle if planned)
+        pre_full = N * N * 8 + 2 * vec_bytes                                # the full dense operator
+        per_step, per_step_full, flops = [], [], []
         for rs in trail:
-            per_step.append(rs.spmv_passes * spmv_b + rs.precond_applies * (N * N * 8 + 2 * vec_bytes))
+            per_step.append(rs.spmv_passes * spmv_b + rs.precond_applies * pre_b)
+            per_step_full.append(rs.spmv_passes * spmv_b + rs.precond_applies * pre_full)
+            flops.append(rs.precond_applies * 2.0 * RANK_R * N * N)
         alg_bytes = float(np.mean(per_step))
+        alg_full = float(np.mean(per_step_full))
         ms_step = ms_total / K
         ach = alg_bytes / (ms_step * 1e-3) / 1e9
         line.update({
@@ -332,8 +337,17 @@ def run_gpu_arm(args):
                          "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": ach / peak,
                          "algorithmic_bytes_per_launch": alg_bytes, "traffic": ncu_traffic("k_optimize"),
                          "traffic_note": "ncu capture of one launch (a 10-tCG step: 11 preconditioner applications)",
-                         "note": "bytes = spmv_passes*(132 nb + 4(n+1) + 96 r n) + precond_applies*(8 N^2 + 16 r N), "
-                                 "averaged over the cycle; the dense (Q+0.1I)^-1 stream dominates"},
+                         "note": "bytes = spmv_passes*(132 nb + 4(n+1) + 96 r n) + precond_applies*(P + 16 r N), averaged "
+                                 "over the cycle; P = unique bytes of the symmetric dense (Q+0.1I)^-1 = 4 N (N+8) when the "
+                                 "upper-triangle kernel is planned, else 8 N^2; the dense stream dominates",
+                         "full_matrix": {"algorithmic_bytes_per_launch": alg_full,
+                                         "achieved": alg_full / (ms_step * 1e-3) / 1e9,
+                                         "frac": alg_full / (ms_step * 1e-3) / 1e9 / peak,
+                                         "note": "same time against the bytes of the full N x N operator (what a "
+                                                 "non-symmetric apply would stream)"},
+                         "fp64": {"useful_tflops": float(np.mean(flops)) / (ms_step * 1e-3) / 1e12,
+                                  "note": "2 r N^2 flops per preconditioner application; the symmetric apply runs on "
+                                          "DMMA m8n8k4 with 5 of 8 M rows used (scripts/dmma_peak.cu measures the pipe)"}},
             "trajectory": [{"f": rs.f_opt, "gradnorm": rs.gradnorm_opt, "tcg": rs.tcg_iterations,
                             "status": rs.tcg_status, "spmv_passes": rs.spmv_passes} for rs in trail],
         })

@@ -83,7 +83,9 @@ SIGNATURES = {
     "dpgo_optimize_result": (C.c_int, [_vp, C.POINTER(OptResult)]),
     "dpgo_spmv_device": (C.c_int, [_vp, _vp, _vp, C.c_int]),
     "dpgo_spmv_algorithmic_bytes": (C.c_int64, [_vp, C.c_int]),
+    "dpgo_precond_algorithmic_bytes": (C.c_int64, [_vp, C.c_int]),
     "dpgo_debug_phase_latency": (C.c_int, [_vp, C.c_int, _dp, _dp]),
+    "dpgo_debug_phase_times": (C.c_int, [_vp, C.c_int, _dp]),
     "dpgo_agent_set_public_poses": (C.c_int, [_vp, C.c_int, _ip]),
     "dpgo_agent_pack_public": (C.c_int, [_vp, _vp]),
     "dpgo_agent_set_shared_edges": (C.c_int, [_vp, C.c_int, _ip, _ip, _ip, _dp, _dp]),

@@ -63,6 +63,7 @@ struct dpgo_problem {
   double *d_S[2] = {nullptr, nullptr};
   double *d_partials = nullptr;
   unsigned *d_bar = nullptr;     // [0] arrival counter, [1] epoch
+  unsigned long long *d_phase_ns = nullptr;   // diagnostic phase clock (8 slots), allocated on request
   dpgo_opt_result_t *d_result = nullptr;
   dpgo_opt_result_t *h_result = nullptr;   // pinned
   bool async_pending = false;
@@ -103,6 +104,9 @@ void fill_kparams(const dpgo_problem *p, dpgo::KParams &kp, int op, const dpgo_o
   kp.partials = p->d_partials;
   kp.bar_counter = p->d_bar;
   kp.bar_epoch = p->d_bar + 1;
+  kp.phase_ns = p->d_phase_ns;
+  static const int dbg_mask = [] { const char *e3 = std::getenv("DPGO_SYM_DEBUG"); return e3 ? std::atoi(e3) : 0; }();
+  kp.dbg = dbg_mask;   // experiments only (skips work: wrong results)
   kp.prm = prm;
   kp.result = p->d_result;
 }
@@ -128,6 +132,7 @@ int ensure_dense(dpgo_problem *p) {
   if (p->dense_per > dpgo::DENSE_PER_MAX)
     return fail(DPGO_ERR_UNSUPPORTED, "dense exact preconditioner: N too large for the per-CTA slab; use block-Jacobi");
   DPGO_CUDA(cudaMalloc(&p->d_dense_part, sizeof(double) * (size_t)p->grid * p->r * N));
+  DPGO_CUDA(cudaMemset(p->d_dense_part, 0, sizeof(double) * (size_t)p->grid * p->r * N));
   DPGO_CUDA(cudaMalloc(&p->d_pinv, N * N * sizeof(double)));
   DPGO_CUDA(cudaMemsetAsync(p->d_pinv, 0, N * N * sizeof(double), p->stream));
   cudaError_t e = dpgo::launch_bsr_to_dense(p->n, p->dh, p->nb, p->d_rowptr, p->d_bcol, p->d_bval, 0.1, p->d_pinv, p->N,
@@ -170,6 +175,7 @@ int ensure_dense(dpgo_problem *p) {
       DPGO_CUDA(cudaMalloc(&p->d_sym_ptr, sizeof(int) * ptr.size()));
       DPGO_CUDA(cudaMalloc(&p->d_sym_g0, sizeof(int) * std::max<size_t>(g0s.size(), 1)));
       DPGO_CUDA(cudaMalloc(&p->d_dense_t2, sizeof(double) * (size_t)p->r * N));
+      DPGO_CUDA(cudaMemset(p->d_dense_t2, 0, sizeof(double) * (size_t)p->r * N));
       DPGO_CUDA(cudaMemcpy(p->d_sym_ptr, ptr.data(), sizeof(int) * ptr.size(), cudaMemcpyHostToDevice));
       DPGO_CUDA(cudaMemcpy(p->d_sym_g0, g0s.data(), sizeof(int) * g0s.size(), cudaMemcpyHostToDevice));
       p->sym_ok = 1;
@@ -452,7 +458,7 @@ int dpgo_problem_destroy(dpgo_problem_t *p) {
   free_dev(p->d_dinv); free_dev(p->d_pinv); free_dev(p->d_dense_part); free_dev(p->d_G);
   free_dev(p->d_dense_t2); free_dev(p->d_sym_ptr); free_dev(p->d_sym_g0);
   for (int i = 0; i < dpgo::V_COUNT; ++i) free_dev(p->d_vec[i]);
-  free_dev(p->d_S[0]); free_dev(p->d_S[1]); free_dev(p->d_partials); free_dev(p->d_bar); free_dev(p->d_result);
+  free_dev(p->d_S[0]); free_dev(p->d_S[1]); free_dev(p->d_partials); free_dev(p->d_bar); free_dev(p->d_phase_ns); free_dev(p->d_result);
   free_dev(p->d_public); free_dev(p->d_pose_ids); free_dev(p->d_pose_ptr); free_dev(p->d_edge_slot);
   free_dev(p->d_edge_out); free_dev(p->d_edge_T); free_dev(p->d_edge_om);
   if (p->h_result) cudaFreeHost(p->h_result);
@@ -781,6 +787,26 @@ int dpgo_debug_phase_latency(dpgo_problem_t *p, int phases, double *us_per_phase
   return DPGO_OK;
 }
 
+int dpgo_debug_phase_times(dpgo_problem_t *p, int enable, double *ms_by_kind) {
+  DPGO_CHECK_HANDLE(p);
+  if (enable && !p->d_phase_ns) {
+    DPGO_CUDA(cudaMalloc(&p->d_phase_ns, 8 * sizeof(unsigned long long)));
+    DPGO_CUDA(cudaMemsetAsync(p->d_phase_ns, 0, 8 * sizeof(unsigned long long), p->stream));
+  }
+  if (p->d_phase_ns) {
+    unsigned long long ns[8];
+    DPGO_CUDA(cudaStreamSynchronize(p->stream));
+    DPGO_CUDA(cudaMemcpy(ns, p->d_phase_ns, sizeof(ns), cudaMemcpyDeviceToHost));
+    if (ms_by_kind)
+      for (int i = 0; i < 8; ++i) ms_by_kind[i] = 1e-6 * (double)ns[i];
+    DPGO_CUDA(cudaMemset(p->d_phase_ns, 0, sizeof(ns)));
+    if (!enable) { cudaFree(p->d_phase_ns); p->d_phase_ns = nullptr; }
+  } else if (ms_by_kind) {
+    for (int i = 0; i < 8; ++i) ms_by_kind[i] = 0.0;
+  }
+  return DPGO_OK;
+}
+
 int dpgo_spmv_device(dpgo_problem_t *p, const double *X_dev, double *out_dev, int add_G) {
   DPGO_CHECK_HANDLE(p);
   DPGO_REQUIRE(X_dev && out_dev, DPGO_ERR_INVALID_ARG, "null argument");
@@ -796,6 +822,17 @@ int64_t dpgo_spmv_algorithmic_bytes(const dpgo_problem_t *p, int add_G) {
   int64_t b = p->nb * (dh * dh * 8 + 4) + ((int64_t)p->n + 1) * 4 + 2 * (int64_t)p->r * dh * p->n * 8;
   if (add_G) b += (int64_t)p->r * dh * p->n * 8;
   return b;
+}
+
+int64_t dpgo_precond_algorithmic_bytes(const dpgo_problem_t *p, int preconditioner) {
+  if (!p) return 0;
+  const int64_t N = (int64_t)p->dh * p->n, vec = (int64_t)p->r * N * 8;
+  if (preconditioner == DPGO_PRECOND_BLOCK_JACOBI) return (int64_t)p->n * 16 * 8 + 2 * vec;
+  if (preconditioner != DPGO_PRECOND_DENSE_EXACT) return 0;
+  // the inverse is symmetric: the unique data is its upper triangle in 8-row groups (what phase_dense_sym reads);
+  // the full-matrix variants read all of it
+  const int64_t mat = p->sym_ok ? (N * N + 8 * N) / 2 * 8 : N * N * 8;
+  return mat + 2 * vec;
 }
 
 // ---- boundary-pose exchange --------------------------------------------------------------------

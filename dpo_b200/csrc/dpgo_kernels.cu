@@ -427,33 +427,37 @@ template <int R> __device__ void phase_dense_sym(const KParams &kp, const double
   const int N = kp.N;
   const int nseg = (N + SYM_SEG - 1) / SYM_SEG;
   const int gp0 = ld_const(kp.sym_ptr + blockIdx.x), ng = ld_const(kp.sym_ptr + blockIdx.x + 1) - gp0;
-  const int *glist = kp.sym_g0 + gp0;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   constexpr int NCW = OPT_THREADS / 32 - 1;             // consumer warps
+  int *sG = reinterpret_cast<int *>(sV + SYM_MAXG * 8 * R);     // first rows of my groups (ascending)
+  const int dbg = kp.dbg;
   // V rows of my groups (direct-product A operands) and the transposed accumulators
-  for (int q = threadIdx.x; q < ng * 8 * R; q += blockDim.x) {
-    const int gi = q / (8 * R), rem = q - gi * 8 * R, rr = rem / R, a = rem - rr * R;
-    const int row = ld_const(glist + gi) + rr;
-    sV[q] = (row < N) ? __ldcg(V + (size_t)row * R + a) : 0.0;
+  if (threadIdx.x < ng) sG[threadIdx.x] = ld_const(kp.sym_g0 + gp0 + threadIdx.x);
+  if (!(dbg & 16)) {
+    for (int q = threadIdx.x; q < ng * 8 * R; q += blockDim.x) {
+      const int gi = q / (8 * R), rem = q - gi * 8 * R, rr = rem / R, a = rem - rr * R;
+      const int row = ld_const(kp.sym_g0 + gp0 + gi) + rr;
+      sV[q] = (row < N) ? __ldcg(V + (size_t)row * R + a) : 0.0;
+    }
+    for (int q = threadIdx.x; q < NCW * ng * 8 * R; q += blockDim.x) sAcc2[q] = 0.0;
   }
-  for (int q = threadIdx.x; q < NCW * ng * 8 * R; q += blockDim.x) sAcc2[q] = 0.0;
   __syncthreads();
   unsigned total = 0;
   for (int sg = 0; sg < nseg; ++sg) {
     const int s1 = min(N, (sg + 1) * SYM_SEG);
-    for (int gi = 0; gi < ng; ++gi) total += (ld_const(glist + gi) < s1) ? 1u : 0u;
+    for (int gi = 0; gi < ng; ++gi) total += (sG[gi] < s1) ? 1u : 0u;
   }
   if (warp == NCW) {
     // ---------------- producer ----------------
-    if (lane == 0) {
+    if (lane == 0 && !(dbg & 2)) {
       uint64_t pol;
       asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
       unsigned c = ring.count;
       for (int sg = 0; sg < nseg; ++sg) {
         const int s0 = sg * SYM_SEG, s1 = min(N, s0 + SYM_SEG);
         for (int gi = 0; gi < ng; ++gi) {
-          const int g0 = ld_const(glist + gi);
-          if (g0 >= s1) continue;
+          const int g0 = sG[gi];
+          if (g0 >= s1) break;                              // ascending: no later group reaches this segment
           const int col_lo = max(s0, g0);
           const unsigned rowbytes = (unsigned)(s1 - col_lo) * 8u;
           const int nrows = min(8, N - g0);
@@ -475,7 +479,7 @@ template <int R> __device__ void phase_dense_sym(const KParams &kp, const double
     // ---------------- consumers ----------------
     const int a = lane >> 2, k = lane & 3;                // A fragment: row a, column k ; D fragment: row a, columns 2k, 2k+1
     const int bn = lane >> 2, bk = lane & 3;              // B fragment: column n = lane>>2, row k = lane&3
-    const int gmin = (ng > 0) ? ld_const(glist) : N;
+    const int gmin = (ng > 0) ? sG[0] : N;
     double *part = kp.dense_part + (size_t)blockIdx.x * R * N;
     unsigned c = ring.count;
     for (int sg = 0; sg < nseg; ++sg) {
@@ -487,14 +491,15 @@ template <int R> __device__ void phase_dense_sym(const KParams &kp, const double
 #pragma unroll
         for (int q = 0; q < 2; ++q) {
           const int col = cw0 + 8 * t + 4 * q + k;
-          va[t][q] = (a < R && col < N) ? __ldcg(V + (size_t)col * R + a) : 0.0;
+          va[t][q] = (a < R && col < N && !(dbg & 4)) ? __ldcg(V + (size_t)col * R + a) : 0.0;
         }
       double D1[4][2];
 #pragma unroll
       for (int t = 0; t < 4; ++t) D1[t][0] = D1[t][1] = 0.0;
       for (int gi = 0; gi < ng; ++gi) {
-        const int g0 = ld_const(glist + gi);
-        if (g0 >= s1) continue;
+        const int g0 = sG[gi];
+        if (g0 >= s1) break;
+        if (dbg & 2) continue;
         const int col_lo = max(s0, g0);
         const int st = c % SYM_NST;
         mbar_wait_parity(&ring.full[st], (c / SYM_NST) & 1);
@@ -505,6 +510,7 @@ template <int R> __device__ void phase_dense_sym(const KParams &kp, const double
 #pragma unroll
         for (int t = 0; t < 4; ++t) {
           const int ctile = cw0 + 8 * t;
+          if (dbg & 1) continue;
           if (ctile < g0 || ctile >= s1) continue;         // warp-uniform: left of the diagonal / past the segment
           const int x = ctile - col_lo;
           // direct: B[kk][n] = P[g0 + 4q + kk][ctile + n]
@@ -525,7 +531,7 @@ template <int R> __device__ void phase_dense_sym(const KParams &kp, const double
         if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_addr(&ring.empty[st])) : "memory");
         ++c;
       }
-      if (a < R) {
+      if (a < R && !(dbg & 8)) {
 #pragma unroll
         for (int t = 0; t < 4; ++t) {
           const int col = cw0 + 8 * t + 2 * k;
@@ -535,22 +541,24 @@ template <int R> __device__ void phase_dense_sym(const KParams &kp, const double
       }
     }
   }
-  ring.count += total;
+  if (!(dbg & 2)) ring.count += total;
   __syncthreads();
   // transposed results: fixed-order sum over the consumer warps
-  for (int q = threadIdx.x; q < ng * 8 * R; q += blockDim.x) {
-    const int gi = q / (8 * R), rem = q - gi * 8 * R, rr = rem / R, a = rem - rr * R;
-    const int row = ld_const(glist + gi) + rr;
-    if (row < N) {
-      double sum = 0.0;
-      for (int w = 0; w < NCW; ++w) sum += sAcc2[((size_t)(w * ng + gi) * 8 + rr) * R + a];
-      kp.dense_t2[(size_t)row * R + a] = sum;
+  if (!(dbg & 16)) {
+    for (int q = threadIdx.x; q < ng * 8 * R; q += blockDim.x) {
+      const int gi = q / (8 * R), rem = q - gi * 8 * R, rr = rem / R, a = rem - rr * R;
+      const int row = sG[gi] + rr;
+      if (row < N) {
+        double sum = 0.0;
+        for (int w = 0; w < NCW; ++w) sum += sAcc2[((size_t)(w * ng + gi) * 8 + rr) * R + a];
+        kp.dense_t2[(size_t)row * R + a] = sum;
+      }
     }
   }
 }
 
 template <int R, int DH>
-__device__ void phase_pz(const KParams &kp, int cb, const double *V, double *Zout, double (&acc)[NRED]) {
+__device__ void phase_pz_old(const KParams &kp, int cb, const double *V, double *Zout, double (&acc)[NRED]) {
   constexpr int TS = R * DH;
   const double *X = kp.v[V_X0 + cb];
   const bool symm = kp.sym_ok != 0;
@@ -595,6 +603,77 @@ __device__ void phase_pz(const KParams &kp, int cb, const double *V, double *Zou
     if (ld) {
       Zout[idx] = z;
       acc[0] = fma(z, __ldcg(V + idx), acc[0]);
+    }
+  }
+}
+
+// Sum of the partial panels + tangent projection.  Step 1 is a flat job over the CTA's contiguous element range
+// [r0*TS, r1*TS): thread (e, p) sums slabs p, p+P, ... of element e with 32 independent L2 loads in flight (P = how
+// many times the range fits into the CTA), fixed order; step 2 combines the P parts in order and projects per pose.
+template <int R, int DH>
+__device__ void phase_pz(const KParams &kp, int cb, const double *V, double *Zout, double *sT, double (&acc)[NRED]) {
+  constexpr int TS = R * DH;
+  constexpr int PZ_TILE = DENSE_PER_MAX * R;          // elements staged per round (sT = the V staging area of the dense phases)
+  const double *X = kp.v[V_X0 + cb];
+  const bool symm = kp.sym_ok != 0;
+  const int nslabs_full = (kp.N + kp.dense_per - 1) / kp.dense_per;
+  const size_t stride = (size_t)R * kp.N;
+  RowIter<R> it(kp);
+  const bool valid = (it.a < R) && (it.c < DH);
+  const int e = it.c * R + it.a;
+  const int rows_per_round = PZ_TILE / TS;
+  for (int rb = it.r0; rb < it.r1; rb += rows_per_round) {
+    const int re = min(it.r1, rb + rows_per_round);
+    const int E = (re - rb) * TS;                                   // flat elements of this round
+    const int P = max(1, min(4, (int)blockDim.x / max(E, 1)));      // slab parts per element (E * P <= PZ_TILE)
+    const size_t base = (size_t)rb * TS;
+    __syncthreads();                                                 // sT free (previous round consumed)
+    for (int q = threadIdx.x; q < E * P; q += blockDim.x) {
+      const int part = q / E, el = q - part * E;
+      const size_t idx = base + el;
+      const int col = (int)(idx / R);
+      const int nslabs = symm ? min(kp.grid, col / 8 + 1) : nslabs_full;
+      // this part's slab range [b0, b1): contiguous, so the overall order stays slab 0, 1, 2, ...
+      const int b0 = (int)((long long)nslabs * part / P), b1 = (int)((long long)nslabs * (part + 1) / P);
+      const double *pp = kp.dense_part + idx;
+      double t = (symm && part == 0) ? __ldcg(kp.dense_t2 + idx) : 0.0;
+      int b = b0;
+      for (; b + 32 <= b1; b += 32) {
+        double tt[32];
+#pragma unroll
+        for (int u = 0; u < 32; ++u) tt[u] = __ldcg(pp + (size_t)(b + u) * stride);
+#pragma unroll
+        for (int u = 0; u < 32; ++u) t += tt[u];
+      }
+      for (; b + 8 <= b1; b += 8) {
+        double tt[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) tt[u] = __ldcg(pp + (size_t)(b + u) * stride);
+#pragma unroll
+        for (int u = 0; u < 8; ++u) t += tt[u];
+      }
+      for (; b < b1; ++b) t += __ldcg(pp + (size_t)b * stride);
+      sT[q] = t;
+    }
+    __syncthreads();
+    for (int jb = rb + (it.jb - it.r0); jb < re; jb += it.stride) {
+      const int j = jb + it.sgw;
+      const bool act = (j < re);
+      const int js = act ? j : re - 1;
+      const bool ld = act && valid;
+      const size_t idx = (size_t)js * TS + e;
+      const double x = ld ? __ldcg(X + idx) : 0.0;
+      double t = 0.0;
+      if (ld) {
+        const int el = (js - rb) * TS + e;
+        for (int part = 0; part < P; ++part) t += sT[part * E + el];
+      }
+      double ya[3], sym[3];
+      const double z = tangent_project_elem<R, DH>(x, t, it.a, it.c, ya, sym);
+      if (ld) {
+        Zout[idx] = z;
+        acc[0] = fma(z, __ldcg(V + idx), acc[0]);
+      }
     }
   }
 }
@@ -705,6 +784,19 @@ template <int R, int DH> __global__ void __launch_bounds__(OPT_THREADS, 1) k_opt
   }
   bc.epoch = *kp.bar_epoch;
   bc.parity = 0;
+  // diagnostic phase clock: CTA 0 / thread 0 charges the time since the previous tick to a phase kind
+  // (0 eval, 1 dense apply, 2 partial sums + projection, 3 Hessian product, 4 tCG update, 5 retraction, 6 final)
+  unsigned long long tick_last = 0;
+  const bool ticking = (kp.phase_ns != nullptr) && blockIdx.x == 0 && threadIdx.x == 0;
+  auto tick = [&](int kind) {
+    if (ticking) {
+      unsigned long long t;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+      if (kind >= 0) kp.phase_ns[kind] += t - tick_last;
+      tick_last = t;
+    }
+  };
+  tick(-1);
   const dpgo_opt_params_t prm = kp.prm;
   const int precond = prm.precond;
   double acc[NRED];
@@ -728,7 +820,7 @@ template <int R, int DH> __global__ void __launch_bounds__(OPT_THREADS, 1) k_opt
       else if (dense_tma) phase_dense_tma<R>(kp, kp.v[V_AUX], sV, ring);
       else phase_dense<R>(kp, kp.v[V_AUX], sV);
       zero(acc); phase_end<0>(kp, bc, acc);
-      zero(acc); phase_pz<R, DH>(kp, 0, kp.v[V_AUX], kp.v[V_Z], acc);
+      zero(acc); phase_pz<R, DH>(kp, 0, kp.v[V_AUX], kp.v[V_Z], sV, acc);
       phase_end<1>(kp, bc, acc);
     } else {
       // reuse phase_update with res := AUX (first = false, alpha = 0 would need RES); do it directly
@@ -766,6 +858,7 @@ template <int R, int DH> __global__ void __launch_bounds__(OPT_THREADS, 1) k_opt
   zero(acc);
   phase_eval<R, DH>(kp, 0, true, precond, acc);
   phase_end(kp, bc, acc);
+  tick(0);
   res.spmv_passes++;
   double f1 = 0.5 * acc[0] + acc[1];
   double gn = sqrt(acc[2]);
@@ -819,8 +912,12 @@ template <int R, int DH> __global__ void __launch_bounds__(OPT_THREADS, 1) k_opt
         else if (dense_tma) phase_dense_tma<R>(kp, kp.v[V_RG0 + cb], sV, ring);
         else phase_dense<R>(kp, kp.v[V_RG0 + cb], sV);
         zero(acc); phase_end<0>(kp, bc, acc);
-        zero(acc); phase_pz<R, DH>(kp, cb, kp.v[V_RG0 + cb], kp.v[V_Z00 + cb], acc);
+        tick(1);
+        zero(acc);
+        if (kp.dbg & 64) phase_pz_old<R, DH>(kp, cb, kp.v[V_RG0 + cb], kp.v[V_Z00 + cb], acc);
+        else phase_pz<R, DH>(kp, cb, kp.v[V_RG0 + cb], kp.v[V_Z00 + cb], sV, acc);
         phase_end<1>(kp, bc, acc);
+        tick(2);
         zr0 = acc[0];
         z0_valid = true;
       }
@@ -839,6 +936,7 @@ template <int R, int DH> __global__ void __launch_bounds__(OPT_THREADS, 1) k_opt
         zero(acc);
         phase_hess<R, DH>(kp, cb, zsrc, kp.v[V_D0 + pd], dnew, beta, true, acc);
         phase_end<1>(kp, bc, acc);
+        tick(3);
         res.spmv_passes++;
         res.tcg_iterations++;
         pd = 1 - pd;
@@ -855,6 +953,7 @@ template <int R, int DH> __global__ void __launch_bounds__(OPT_THREADS, 1) k_opt
         zero(acc);
         phase_update<R, DH>(kp, cb, dcur, alpha, eta_zero, precond, acc);
         phase_end<2>(kp, bc, acc);
+        tick(4);
         eta_zero = false;
         const double nr = sqrt(acc[0]);
         const double n0t = n0;                         // n0^theta, theta = 1
@@ -868,8 +967,12 @@ template <int R, int DH> __global__ void __launch_bounds__(OPT_THREADS, 1) k_opt
           else if (dense_tma) phase_dense_tma<R>(kp, kp.v[V_RES], sV, ring);
           else phase_dense<R>(kp, kp.v[V_RES], sV);
           zero(acc); phase_end<0>(kp, bc, acc);
-          zero(acc); phase_pz<R, DH>(kp, cb, kp.v[V_RES], kp.v[V_Z], acc);
+          tick(1);
+          zero(acc);
+          if (kp.dbg & 64) phase_pz_old<R, DH>(kp, cb, kp.v[V_RES], kp.v[V_Z], acc);
+          else phase_pz<R, DH>(kp, cb, kp.v[V_RES], kp.v[V_Z], sV, acc);
           phase_end<1>(kp, bc, acc);
+          tick(2);
           zr_new = acc[0];
         }
         res.precond_applies++;
@@ -885,10 +988,12 @@ template <int R, int DH> __global__ void __launch_bounds__(OPT_THREADS, 1) k_opt
       zero(acc);
       phase_retract<R, DH>(kp, cb, 0, dcur, tau, eta_zero, 0.0, acc);
       phase_end<2>(kp, bc, acc);
+      tick(5);
       const double denom = -acc[0] - 0.5 * acc[1];
       zero(acc);
       phase_eval<R, DH>(kp, 1 - cb, false, precond, acc);
       phase_end(kp, bc, acc);
+      tick(0);
       res.spmv_passes++;
       const double f2 = 0.5 * acc[0] + acc[1];
       const double gn2 = sqrt(acc[2]);
@@ -925,6 +1030,7 @@ template <int R, int DH> __global__ void __launch_bounds__(OPT_THREADS, 1) k_opt
   zero(acc);
   phase_final<R, DH>(kp, cur, acc);
   phase_end<1>(kp, bc, acc);
+  tick(6);
   res.relative_change = sqrt(acc[0] / (double)kp.n);
   res.success = 1;
   if (blockIdx.x == 0 && threadIdx.x == 0) { *kp.result = res; *kp.bar_epoch = bc.epoch; }

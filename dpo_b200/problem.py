@@ -223,6 +223,9 @@ class QuadraticProblem:
     def spmv_algorithmic_bytes(self, add_G: bool = False) -> int:
         return int(self._lib.dpgo_spmv_algorithmic_bytes(self._h, int(add_G)))
 
+    def precond_algorithmic_bytes(self, preconditioner: int) -> int:
+        return int(self._lib.dpgo_precond_algorithmic_bytes(self._h, int(preconditioner)))
+
     def resident_f_gradnorm(self):
         fo, nrm = C.c_double(), C.c_double()
         capi.check(self._lib.dpgo_agent_f_rgradnorm_resident(self._h, C.byref(fo), C.byref(nrm)))

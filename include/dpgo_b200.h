@@ -182,8 +182,17 @@ DPGO_API int dpgo_optimize_result(dpgo_problem_t *p, dpgo_opt_result_t *result);
 /* the Q.X product kernel alone on device buffers (the roofline kernel): Out = X Q (+ G) */
 DPGO_API int dpgo_spmv_device(dpgo_problem_t *p, const double *X_dev, double *out_dev, int add_G);
 DPGO_API int64_t dpgo_spmv_algorithmic_bytes(const dpgo_problem_t *p, int add_G);
+/* bytes one application of the preconditioner (ref: QuadraticProblem::PreConditioner, src/QuadraticProblem.cpp:75-87)
+ * has to move: the operator's unique data (upper triangle of the symmetric dense inverse when the symmetric
+ * kernel is planned, i.e. after the first exact-mode optimise; the full matrix otherwise) + input and output vector */
+DPGO_API int64_t dpgo_precond_algorithmic_bytes(const dpgo_problem_t *p, int preconditioner);
 /* diagnostic: cost of one empty phase of the persistent kernel (grid barrier + scalar reduction) and of its launch */
 DPGO_API int dpgo_debug_phase_latency(dpgo_problem_t *p, int phases, double *us_per_phase, double *us_launch);
+/* diagnostic: phase clock of the persistent kernel.  enable != 0 switches it on (subsequent optimise calls
+ * accumulate, per phase kind, the nanoseconds CTA 0 spent up to the closing grid barrier); every call returns the
+ * accumulated milliseconds in ms_by_kind[8] (0 eval pass, 1 dense preconditioner apply, 2 partial sums + projection,
+ * 3 Hessian product, 4 tCG update, 5 retraction, 6 final, 7 unused) and resets them; enable == 0 switches it off. */
+DPGO_API int dpgo_debug_phase_times(dpgo_problem_t *p, int enable, double *ms_by_kind);
 
 /* ---- boundary-pose exchange (multi-agent, one agent per GPU) ----------------------------- */
 /* ref: PGOAgent::getSharedPoseDict, src/PGOAgent.cpp:95-105: register which local poses are

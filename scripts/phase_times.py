@@ -1,0 +1,72 @@
+#!/usr/bin/env python
+"""Phase clock of k_optimize on the bench workload (sphere2500, 1 agent, r = 5, exact preconditioner): where one
+RTR step spends its time, per phase kind, as seen by CTA 0 up to each closing grid barrier
+(dpgo_debug_phase_times).  Prints one JSON line; --dataset / --rank / --precond select other workloads."""
+import argparse
+import ctypes as C
+import json
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import numpy as np
+import torch
+import dpo_b200 as dp
+from dpo_b200 import posegraph as pg, _capi
+
+KINDS = ["eval", "dense_apply", "partial_sums_project", "hessian", "tcg_update", "retract", "final", "unused"]
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--dataset", default="sphere2500")
+    ap.add_argument("--rank", type=int, default=5)
+    ap.add_argument("--precond", default="exact", choices=["exact", "jacobi"])
+    ap.add_argument("--steps", type=int, default=30)
+    args = ap.parse_args()
+    edges, n = pg.read_g2o_file(os.path.join(ROOT, "data", args.dataset + ".g2o"))
+    d = edges.d
+    X0 = pg.fixedStiefelVariable(d, args.rank) @ pg.chordalInitialization(d, n, edges)
+    prob = dp.QuadraticProblem(n, d, args.rank)
+    prob.setQ_blocks(*pg.connection_laplacian_blocks(edges))
+    prob.set_stream(torch.cuda.current_stream().cuda_stream)
+    opt = dp.QuadraticOptimizer(prob)
+    opt.setTrustRegionTolerance(1e-2)
+    opt.setTrustRegionIterations(1)
+    opt.setTrustRegionMaxInnerIterations(10)
+    opt.setTrustRegionInitialRadius(100)
+    opt.setPreconditioner(dp.PRECOND_DENSE_EXACT if args.precond == "exact" else dp.PRECOND_BLOCK_JACOBI)
+    X0d = torch.from_numpy(np.asfortranarray(X0).ravel(order="F").copy()).cuda()
+
+    def steps(count):
+        applies = passes = 0
+        for i in range(count):
+            if i % 6 == 0:
+                prob.copy_X_from_device(X0d.data_ptr())
+            opt.optimize_resident_async()
+            r = opt.fetch_result()
+            applies += r.precond_applies
+            passes += r.spmv_passes
+        return applies, passes
+
+    steps(6)
+    ms = (C.c_double * 8)()
+    _capi.check(prob._lib.dpgo_debug_phase_times(prob._h, 1, ms))
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record()
+    applies, passes = steps(args.steps)
+    e1.record()
+    torch.cuda.synchronize()
+    _capi.check(prob._lib.dpgo_debug_phase_times(prob._h, 0, ms))
+    out = {"workload": f"{args.dataset} 1 agent r={args.rank} {args.precond}", "steps": args.steps,
+           "ms_per_step_events": e0.elapsed_time(e1) / args.steps, "precond_applies": applies, "q_passes": passes,
+           "ms_per_step_by_kind": {k: ms[i] / args.steps for i, k in enumerate(KINDS) if ms[i] > 0},
+           "us_per_dense_apply": 1e3 * ms[1] / max(applies, 1), "us_per_partial_sum": 1e3 * ms[2] / max(applies, 1),
+           "us_per_hessian": 1e3 * ms[3] / max(passes - 2 * args.steps, 1)}
+    print(json.dumps(out))
+
+
+if __name__ == "__main__":
+    main()
