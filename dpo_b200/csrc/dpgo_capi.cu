@@ -56,7 +56,7 @@ struct dpgo_problem {
   double *d_bval = nullptr, *d_dinv = nullptr, *d_pinv = nullptr, *d_dense_part = nullptr, *d_dense_t2 = nullptr;
   int dense_per = 1;
   int sym_ok = 0;                // symmetric (upper-triangle) dense preconditioner planned
-  int *d_sym_ptr = nullptr, *d_sym_g0 = nullptr;
+  int *d_sym_cut = nullptr, *d_sym_segptr = nullptr, *d_sym_cfirst = nullptr, *d_sym_ccount = nullptr;
   // vectors
   double *d_G = nullptr;
   double *d_vec[dpgo::V_COUNT] = {};
@@ -93,8 +93,10 @@ void fill_kparams(const dpgo_problem *p, dpgo::KParams &kp, int op, const dpgo_o
   kp.dense_part = p->d_dense_part;
   kp.dense_per = p->dense_per;
   kp.sym_ok = p->sym_ok;
-  kp.sym_ptr = p->d_sym_ptr;
-  kp.sym_g0 = p->d_sym_g0;
+  kp.sym_cut = p->d_sym_cut;
+  kp.sym_segptr = p->d_sym_segptr;
+  kp.sym_cfirst = p->d_sym_cfirst;
+  kp.sym_ccount = p->d_sym_ccount;
   kp.dense_t2 = p->d_dense_t2;
   kp.cta_rows = p->d_cta_rows;
   kp.G = p->d_G;
@@ -143,41 +145,63 @@ int ensure_dense(dpgo_problem *p) {
     free_dev(p->d_dense_part);
     return fail(DPGO_ERR_CUDA, std::string("dense preconditioner setup: ") + cudaGetErrorString(e));
   }
-  // Plan of the symmetric (upper-triangle) variant: rows in groups of 8, group g streams columns >= 8g only.
-  // Group b goes to CTA b first (so CTA b's panel starts at column 8b -- phase_pz relies on it), the remaining
-  // groups by decreasing trapezoid area to the least-loaded CTA (LPT).  Used for even N >= 2048 when no CTA gets
-  // more than 16 groups and the imbalance stays small; otherwise the full-matrix stream is used.
+  // Plan of the symmetric (upper-triangle) variant (phase_dense_sym): chunks (segment J of 480 columns, 8-row group g
+  // with 8g < end of J) in segment-major order, cut into `grid` contiguous runs of equal cost (streamed columns + a
+  // fixed per-chunk cost); per segment the consecutive CTAs that touch it get the partial-panel slots 0..ccount-1.
   static const bool no_sym = [] { const char *e2 = std::getenv("DPGO_DENSE_FULL"); return e2 && e2[0] == '1'; }();
   p->sym_ok = 0;
   if (!no_sym && (N % 2 == 0) && N >= 2048) {
-    const int G = p->grid, NG = (int)((N + 7) / 8);
-    std::vector<std::vector<int>> lists((size_t)G);
-    std::vector<double> load((size_t)G, 0.0);
-    for (int g = 0; g < NG; ++g) {
-      int best = 0;
-      if (g < G) best = g;
-      else
-        for (int b = 1; b < G; ++b)
-          if (load[(size_t)b] < load[(size_t)best]) best = b;
-      lists[(size_t)best].push_back(8 * g);
-      load[(size_t)best] += (double)((int)N - 8 * g);
+    const int G = p->grid, SEG = 480, nseg = (int)((N + SEG - 1) / SEG);
+    std::vector<int> segptr((size_t)nseg + 1, 0);
+    for (int J = 0; J < nseg; ++J) {
+      const int s1 = (int)std::min<int64_t>(N, (int64_t)(J + 1) * SEG);
+      segptr[(size_t)J + 1] = segptr[(size_t)J] + (s1 + 7) / 8;
     }
-    size_t maxg = 0;
-    double lmax = 0, lsum = 0;
-    for (int b = 0; b < G; ++b) { maxg = std::max(maxg, lists[(size_t)b].size()); lmax = std::max(lmax, load[(size_t)b]); lsum += load[(size_t)b]; }
-    if (maxg <= 16 && lmax <= 1.15 * lsum / G) {
-      std::vector<int> ptr((size_t)G + 1, 0), g0s;
-      for (int b = 0; b < G; ++b) {
-        std::sort(lists[(size_t)b].begin(), lists[(size_t)b].end());
-        g0s.insert(g0s.end(), lists[(size_t)b].begin(), lists[(size_t)b].end());
-        ptr[(size_t)b + 1] = (int)g0s.size();
+    const int nchunks = segptr[(size_t)nseg];
+    std::vector<double> cum((size_t)nchunks + 1, 0.0);
+    {
+      int lin = 0;
+      for (int J = 0; J < nseg; ++J) {
+        const int s0 = J * SEG, s1 = (int)std::min<int64_t>(N, (int64_t)s0 + SEG);
+        for (int g = 0; 8 * g < s1; ++g, ++lin) cum[(size_t)lin + 1] = cum[(size_t)lin] + (double)(s1 - std::max(s0, 8 * g)) + 48.0;
       }
-      DPGO_CUDA(cudaMalloc(&p->d_sym_ptr, sizeof(int) * ptr.size()));
-      DPGO_CUDA(cudaMalloc(&p->d_sym_g0, sizeof(int) * std::max<size_t>(g0s.size(), 1)));
-      DPGO_CUDA(cudaMalloc(&p->d_dense_t2, sizeof(double) * (size_t)p->r * N));
-      DPGO_CUDA(cudaMemset(p->d_dense_t2, 0, sizeof(double) * (size_t)p->r * N));
-      DPGO_CUDA(cudaMemcpy(p->d_sym_ptr, ptr.data(), sizeof(int) * ptr.size(), cudaMemcpyHostToDevice));
-      DPGO_CUDA(cudaMemcpy(p->d_sym_g0, g0s.data(), sizeof(int) * g0s.size(), cudaMemcpyHostToDevice));
+    }
+    std::vector<int> cut((size_t)G + 1, 0);
+    {
+      int lin = 0;
+      for (int b = 1; b < G; ++b) {
+        const double target = cum[(size_t)nchunks] * b / G;
+        while (lin < nchunks && cum[(size_t)lin + 1] <= target) ++lin;
+        cut[(size_t)b] = lin;
+      }
+      cut[(size_t)G] = nchunks;
+    }
+    std::vector<int> cfirst((size_t)nseg, 0), ccount((size_t)nseg, 0);
+    int maxslots = 0;
+    for (int J = 0; J < nseg; ++J) {
+      int first = -1, last = -1;
+      for (int b = 0; b < G; ++b)
+        if (cut[(size_t)b] < segptr[(size_t)J + 1] && cut[(size_t)b + 1] > segptr[(size_t)J] && cut[(size_t)b] < cut[(size_t)b + 1]) {
+          if (first < 0) first = b;
+          last = b;
+        }
+      cfirst[(size_t)J] = std::max(first, 0);
+      ccount[(size_t)J] = (first < 0) ? 0 : last - first + 1;
+      maxslots = std::max(maxslots, ccount[(size_t)J]);
+    }
+    bool runs_ok = (maxslots <= G);   // the panels live in dense_part (grid x r x N)
+    for (int b = 0; b < G; ++b) runs_ok = runs_ok && (cut[(size_t)b] < cut[(size_t)b + 1]);   // slots assume no empty run
+    if (runs_ok) {
+      DPGO_CUDA(cudaMalloc(&p->d_sym_cut, sizeof(int) * cut.size()));
+      DPGO_CUDA(cudaMalloc(&p->d_sym_segptr, sizeof(int) * segptr.size()));
+      DPGO_CUDA(cudaMalloc(&p->d_sym_cfirst, sizeof(int) * cfirst.size()));
+      DPGO_CUDA(cudaMalloc(&p->d_sym_ccount, sizeof(int) * ccount.size()));
+      DPGO_CUDA(cudaMalloc(&p->d_dense_t2, sizeof(double) * (size_t)nseg * p->r * N));
+      DPGO_CUDA(cudaMemset(p->d_dense_t2, 0, sizeof(double) * (size_t)nseg * p->r * N));
+      DPGO_CUDA(cudaMemcpy(p->d_sym_cut, cut.data(), sizeof(int) * cut.size(), cudaMemcpyHostToDevice));
+      DPGO_CUDA(cudaMemcpy(p->d_sym_segptr, segptr.data(), sizeof(int) * segptr.size(), cudaMemcpyHostToDevice));
+      DPGO_CUDA(cudaMemcpy(p->d_sym_cfirst, cfirst.data(), sizeof(int) * cfirst.size(), cudaMemcpyHostToDevice));
+      DPGO_CUDA(cudaMemcpy(p->d_sym_ccount, ccount.data(), sizeof(int) * ccount.size(), cudaMemcpyHostToDevice));
       p->sym_ok = 1;
     }
   }
@@ -289,7 +313,7 @@ int build_from_triplets(dpgo_problem *p, std::vector<BlockTriplet> &trip, unsign
   cudaSetDevice(p->device);
   free_dev(p->d_rowptr); free_dev(p->d_bcol); free_dev(p->d_bval); free_dev(p->d_dinv); free_dev(p->d_pinv);
   free_dev(p->d_cta_rows); free_dev(p->d_partials); free_dev(p->d_dense_part); free_dev(p->d_groups);
-  free_dev(p->d_dense_t2); free_dev(p->d_sym_ptr); free_dev(p->d_sym_g0);
+  free_dev(p->d_dense_t2); free_dev(p->d_sym_cut); free_dev(p->d_sym_segptr); free_dev(p->d_sym_cfirst); free_dev(p->d_sym_ccount);
   p->sym_ok = 0;
   p->have_Q = false;
   p->ngroups = 0;
@@ -456,7 +480,7 @@ int dpgo_problem_destroy(dpgo_problem_t *p) {
   if (p->stream) cudaStreamSynchronize(p->stream);
   free_dev(p->d_rowptr); free_dev(p->d_bcol); free_dev(p->d_cta_rows); free_dev(p->d_bval); free_dev(p->d_groups);
   free_dev(p->d_dinv); free_dev(p->d_pinv); free_dev(p->d_dense_part); free_dev(p->d_G);
-  free_dev(p->d_dense_t2); free_dev(p->d_sym_ptr); free_dev(p->d_sym_g0);
+  free_dev(p->d_dense_t2); free_dev(p->d_sym_cut); free_dev(p->d_sym_segptr); free_dev(p->d_sym_cfirst); free_dev(p->d_sym_ccount);
   for (int i = 0; i < dpgo::V_COUNT; ++i) free_dev(p->d_vec[i]);
   free_dev(p->d_S[0]); free_dev(p->d_S[1]); free_dev(p->d_partials); free_dev(p->d_bar); free_dev(p->d_phase_ns); free_dev(p->d_result);
   free_dev(p->d_public); free_dev(p->d_pose_ids); free_dev(p->d_pose_ptr); free_dev(p->d_edge_slot);

@@ -301,7 +301,7 @@ template <int R> __device__ void phase_dense(const KParams &kp, const double *V,
 constexpr int DENSE_NST = 6;
 constexpr int DENSE_CONS = OPT_THREADS - 32;          // 480 consumer threads
 constexpr int DENSE_SEG = DENSE_CONS * 4;             // 1920 columns per chunk
-constexpr int DENSE_RING_DOUBLES = 3 * 8 * ((OPT_THREADS / 32 - 1) * 32 + 4);   // max(6 x 1920, 3 x 8 x 484) doubles
+constexpr int DENSE_RING_DOUBLES = 5 * (8 * ((OPT_THREADS / 32 - 1) * 32 + 4) + 8 * 5);   // max(6 x 1920, the symmetric variant's 5 stages) doubles
 static_assert(DENSE_RING_DOUBLES >= DENSE_NST * DENSE_SEG, "ring must hold the full-matrix stages too");
 
 struct DenseRing {
@@ -403,87 +403,93 @@ template <int R> __device__ void phase_dense_tma(const KParams &kp, const double
 }
 
 // ---- symmetric variant: read only the upper triangle of Pinv --------------------------------------------------
-// T = V * Pinv with Pinv symmetric.  The rows are cut into groups of 8; a group g (rows g0..g0+7) streams only the
-// columns c >= g0 of its rows (upper trapezoid: half the bytes).  Every 8x8 tile right of the diagonal feeds TWO
-// products from shared memory:
-//   direct      T[:, ctile..] += V[:, g0..]   * P[g0.., ctile..]      (accumulated per column, over the CTA's groups)
-//   transposed  T[:, g0..]    += V[:, ctile..] * P[g0.., ctile..]^T    (accumulated per row group)
+// T = V * Pinv with Pinv symmetric.  The matrix is cut into column segments of SYM_SEG = 480 columns and row groups
+// of 8 rows; a chunk (J, g) is the 8 x <=480 piece of group g inside segment J, restricted to columns >= 8g (upper
+// trapezoid: half the bytes).  Every 8x8 tile right of the diagonal feeds TWO products from shared memory:
+//   direct      T[:, ctile..] += V[:, g0..]   * P[g0.., ctile..]      (per column; registers, summed over the groups)
+//   transposed  T[:, g0..]    += V[:, ctile..] * P[g0.., ctile..]^T    (per chunk; summed over the 15 consumer warps)
 // and the diagonal tile feeds the direct product only.  Both are mma.sync m8n8k4 (DMMA): the 8x8 tile is read from
 // shared memory in the two B-fragment layouts, so the k-reduction of the transposed product happens inside the tensor
-// op -- no cross-lane reduction per element.  Groups are dealt to CTAs by decreasing trapezoid area (LPT, host side,
-// <1-5 % imbalance); per CTA the direct partials form one panel (as in the full variant), the transposed results
-// are complete per row group after a fixed-order sum over the 15 consumer warps.  Same producer/consumer ring.
-constexpr int SYM_NST = 3;
+// op.  The chunks are ordered segment-major and the host cuts that sequence into `grid` contiguous runs of equal
+// streamed bytes (+ a fixed cost per chunk), so a CTA works inside one or two segments:
+//   * direct partials: one panel slot per (CTA, segment) -- ~grid/nseg+1 slots per column instead of `grid`;
+//   * transposed results: chunk (J, g) is owned by exactly one CTA, which writes rows 8g..8g+7 of slot J of dense_t2.
+// phase_pz adds, per element, the <= ccount[J] panel slots and the <= nseg transposed slots in fixed order.
+// Warp 15 is the producer (bulk TMA: 8 row pieces + the 8 V columns of the group per chunk, L2 evict-first for the
+// matrix), warps 0..14 consume through full/empty mbarriers; the consumers park their transposed fragments in shared
+// memory and meet at a named barrier once per SYM_WIN chunks to sum them over the warps.
+constexpr int SYM_NST = 5;
 constexpr int SYM_SEG = (OPT_THREADS / 32 - 1) * 32;   // 480 columns per segment: 32 per consumer warp
 constexpr int SYM_SROW = SYM_SEG + 4;                   // staged row pitch: 3872 B = 32 mod 128 (conflict-light tile reads)
-constexpr int SYM_STAGE = 8 * SYM_SROW;                 // doubles per stage (8 rows)
-constexpr int SYM_MAXG = 16;                            // row groups per CTA (host falls back beyond)
+constexpr int SYM_VOFF = 8 * SYM_SROW;                  // the group's V columns (8 x R doubles) follow the 8 rows
+constexpr int SYM_STAGE = SYM_VOFF + 8 * 5;             // doubles per stage (R <= 5)
+constexpr int SYM_RING_DOUBLES = SYM_NST * SYM_STAGE;
+static_assert(SYM_RING_DOUBLES <= DENSE_RING_DOUBLES && SYM_NST <= DENSE_NST, "ring too small for the symmetric variant");
+constexpr int SYM_WIN = 8;                              // chunks per transposed-fragment window
+constexpr int SYM_META_DOUBLES = SYM_WIN;               // 2 ints per window slot: segment, first row
+static_assert((OPT_THREADS / 32 - 1) * SYM_WIN * 8 * 5 <= DENSE_PER_MAX * 5, "the fragment window lives in the V staging area");
 
 __device__ __forceinline__ void dmma884(double &d0, double &d1, double a, double b) {
   asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
 }
 
-template <int R> __device__ void phase_dense_sym(const KParams &kp, const double *V, double *sV, DenseRing &ring, double *sAcc2) {
+template <int R> __device__ void phase_dense_sym(const KParams &kp, const double *V, DenseRing &ring, double *sAcc, int *sMeta) {
   const int N = kp.N;
   const int nseg = (N + SYM_SEG - 1) / SYM_SEG;
-  const int gp0 = ld_const(kp.sym_ptr + blockIdx.x), ng = ld_const(kp.sym_ptr + blockIdx.x + 1) - gp0;
+  const int lin0 = ld_const(kp.sym_cut + blockIdx.x), lin1 = ld_const(kp.sym_cut + blockIdx.x + 1);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   constexpr int NCW = OPT_THREADS / 32 - 1;             // consumer warps
-  int *sG = reinterpret_cast<int *>(sV + SYM_MAXG * 8 * R);     // first rows of my groups (ascending)
   const int dbg = kp.dbg;
-  // V rows of my groups (direct-product A operands) and the transposed accumulators
-  if (threadIdx.x < ng) sG[threadIdx.x] = ld_const(kp.sym_g0 + gp0 + threadIdx.x);
-  if (!(dbg & 16)) {
-    for (int q = threadIdx.x; q < ng * 8 * R; q += blockDim.x) {
-      const int gi = q / (8 * R), rem = q - gi * 8 * R, rr = rem / R, a = rem - rr * R;
-      const int row = ld_const(kp.sym_g0 + gp0 + gi) + rr;
-      sV[q] = (row < N) ? __ldcg(V + (size_t)row * R + a) : 0.0;
-    }
-    for (int q = threadIdx.x; q < NCW * ng * 8 * R; q += blockDim.x) sAcc2[q] = 0.0;
-  }
-  __syncthreads();
-  unsigned total = 0;
-  for (int sg = 0; sg < nseg; ++sg) {
-    const int s1 = min(N, (sg + 1) * SYM_SEG);
-    for (int gi = 0; gi < ng; ++gi) total += (sG[gi] < s1) ? 1u : 0u;
-  }
+  int J0 = 0;
+  while (J0 + 1 < nseg && ld_const(kp.sym_segptr + J0 + 1) <= lin0) ++J0;
   if (warp == NCW) {
     // ---------------- producer ----------------
     if (lane == 0 && !(dbg & 2)) {
       uint64_t pol;
       asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
       unsigned c = ring.count;
-      for (int sg = 0; sg < nseg; ++sg) {
-        const int s0 = sg * SYM_SEG, s1 = min(N, s0 + SYM_SEG);
-        for (int gi = 0; gi < ng; ++gi) {
-          const int g0 = sG[gi];
-          if (g0 >= s1) break;                              // ascending: no later group reaches this segment
+      int lin = lin0;
+      for (int J = J0; J < nseg && lin < lin1; ++J) {
+        const int s0 = J * SYM_SEG, s1 = min(N, s0 + SYM_SEG);
+        const int p0 = ld_const(kp.sym_segptr + J), p1 = ld_const(kp.sym_segptr + J + 1);
+        const int gb = min(p1, lin1) - p0;
+        for (int g = lin - p0; g < gb; ++g) {
+          const int g0 = 8 * g;
           const int col_lo = max(s0, g0);
           const unsigned rowbytes = (unsigned)(s1 - col_lo) * 8u;
           const int nrows = min(8, N - g0);
+          const unsigned vbytes = (unsigned)(nrows * R) * 8u;
           const int st = c % SYM_NST;
           if (c >= SYM_NST) mbar_wait_parity(&ring.empty[st], ((c / SYM_NST) - 1) & 1);
+          double *stage = ring.buf + (size_t)st * SYM_STAGE;
           asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(&ring.full[st])),
-                       "r"(rowbytes * (unsigned)nrows)
+                       "r"(rowbytes * (unsigned)nrows + vbytes)
+                       : "memory");
+          asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                           smem_addr(stage + SYM_VOFF)),
+                       "l"(V + (size_t)g0 * R), "r"(vbytes), "r"(smem_addr(&ring.full[st]))
                        : "memory");
           for (int rr = 0; rr < nrows; ++rr)
             asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(
-                             smem_addr(ring.buf + (size_t)st * SYM_STAGE + (size_t)rr * SYM_SROW)),
+                             smem_addr(stage + (size_t)rr * SYM_SROW)),
                          "l"(kp.pinv + (size_t)(g0 + rr) * N + col_lo), "r"(rowbytes), "r"(smem_addr(&ring.full[st])), "l"(pol)
                          : "memory");
           ++c;
         }
+        lin = p0 + gb;
       }
     }
   } else {
     // ---------------- consumers ----------------
     const int a = lane >> 2, k = lane & 3;                // A fragment: row a, column k ; D fragment: row a, columns 2k, 2k+1
     const int bn = lane >> 2, bk = lane & 3;              // B fragment: column n = lane>>2, row k = lane&3
-    const int gmin = (ng > 0) ? sG[0] : N;
-    double *part = kp.dense_part + (size_t)blockIdx.x * R * N;
     unsigned c = ring.count;
-    for (int sg = 0; sg < nseg; ++sg) {
-      const int s0 = sg * SYM_SEG, s1 = min(N, s0 + SYM_SEG);
+    const unsigned c_begin = c;
+    int lin = lin0;
+    for (int J = J0; J < nseg && lin < lin1; ++J) {
+      const int s0 = J * SYM_SEG, s1 = min(N, s0 + SYM_SEG);
+      const int p0 = ld_const(kp.sym_segptr + J), p1 = ld_const(kp.sym_segptr + J + 1);
+      const int gb = min(p1, lin1) - p0;
       const int cw0 = s0 + 32 * warp;
       double va[4][2];                                    // transposed-product A operands: V[a, ctile + 4q + k]
 #pragma unroll
@@ -491,120 +497,82 @@ template <int R> __device__ void phase_dense_sym(const KParams &kp, const double
 #pragma unroll
         for (int q = 0; q < 2; ++q) {
           const int col = cw0 + 8 * t + 4 * q + k;
-          va[t][q] = (a < R && col < N && !(dbg & 4)) ? __ldcg(V + (size_t)col * R + a) : 0.0;
+          va[t][q] = (a < R && col < N) ? __ldcg(V + (size_t)col * R + a) : 0.0;
         }
       double D1[4][2];
 #pragma unroll
       for (int t = 0; t < 4; ++t) D1[t][0] = D1[t][1] = 0.0;
-      for (int gi = 0; gi < ng; ++gi) {
-        const int g0 = sG[gi];
-        if (g0 >= s1) break;
-        if (dbg & 2) continue;
-        const int col_lo = max(s0, g0);
-        const int st = c % SYM_NST;
-        mbar_wait_parity(&ring.full[st], (c / SYM_NST) & 1);
-        const double *base = ring.buf + (size_t)st * SYM_STAGE;
-        const double a1_0 = (a < R) ? sV[(gi * 8 + k) * R + a] : 0.0;          // V[a, g0 + k]
-        const double a1_1 = (a < R) ? sV[(gi * 8 + 4 + k) * R + a] : 0.0;      // V[a, g0 + 4 + k]
+      for (int g = lin - p0; g < gb; ++g) {
+        const int g0 = 8 * g;
         double D2_0 = 0.0, D2_1 = 0.0;
+        if (!(dbg & 2)) {
+          const int col_lo = max(s0, g0);
+          const int st = c % SYM_NST;
+          mbar_wait_parity(&ring.full[st], (c / SYM_NST) & 1);
+          const double *base = ring.buf + (size_t)st * SYM_STAGE;
+          const double a1_0 = (a < R && g0 + k < N) ? base[SYM_VOFF + k * R + a] : 0.0;            // V[a, g0 + k]
+          const double a1_1 = (a < R && g0 + 4 + k < N) ? base[SYM_VOFF + (4 + k) * R + a] : 0.0;  // V[a, g0 + 4 + k]
 #pragma unroll
-        for (int t = 0; t < 4; ++t) {
-          const int ctile = cw0 + 8 * t;
-          if (dbg & 1) continue;
-          if (ctile < g0 || ctile >= s1) continue;         // warp-uniform: left of the diagonal / past the segment
-          const int x = ctile - col_lo;
-          // direct: B[kk][n] = P[g0 + 4q + kk][ctile + n]
-          dmma884(D1[t][0], D1[t][1], a1_0, base[(size_t)bk * SYM_SROW + x + bn]);
-          dmma884(D1[t][0], D1[t][1], a1_1, base[(size_t)(4 + bk) * SYM_SROW + x + bn]);
-          if (ctile > g0) {
-            // transposed: B[c'][n] = P[g0 + n][ctile + 4q + c']
-            dmma884(D2_0, D2_1, va[t][0], base[(size_t)bn * SYM_SROW + x + bk]);
-            dmma884(D2_0, D2_1, va[t][1], base[(size_t)bn * SYM_SROW + x + 4 + bk]);
+          for (int t = 0; t < 4; ++t) {
+            const int ctile = cw0 + 8 * t;
+            if (dbg & 1) continue;
+            if (ctile < g0 || ctile >= s1) continue;         // warp-uniform: left of the diagonal / past the segment
+            const int x = ctile - col_lo;
+            // direct: B[kk][n] = P[g0 + 4q + kk][ctile + n]
+            dmma884(D1[t][0], D1[t][1], a1_0, base[(size_t)bk * SYM_SROW + x + bn]);
+            dmma884(D1[t][0], D1[t][1], a1_1, base[(size_t)(4 + bk) * SYM_SROW + x + bn]);
+            if (ctile > g0) {
+              // transposed: B[c'][n] = P[g0 + n][ctile + 4q + c']
+              dmma884(D2_0, D2_1, va[t][0], base[(size_t)bn * SYM_SROW + x + bk]);
+              dmma884(D2_0, D2_1, va[t][1], base[(size_t)bn * SYM_SROW + x + 4 + bk]);
+            }
           }
+          __syncwarp();
+          if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_addr(&ring.empty[st])) : "memory");
         }
-        if (a < R) {                                        // rows g0 + 2k, g0 + 2k + 1 of the transposed result
-          double *acc2 = sAcc2 + ((size_t)(warp * ng + gi) * 8 + 2 * k) * R + a;
-          acc2[0] += D2_0;
-          acc2[R] += D2_1;
+        // transposed result of this chunk: rows g0 + 2k, g0 + 2k + 1 (fragment columns), component a.  The fragments of
+        // SYM_WIN consecutive chunks are parked per warp in shared memory; every SYM_WIN chunks (and after the CTA's
+        // last chunk) the consumers meet and sum them over the warps in fixed order: 2 named barriers per window.
+        const int slot = (int)(c - c_begin) % SYM_WIN;
+        double *frag = sAcc + (size_t)((warp * SYM_WIN + slot) * 8) * R;
+        if (a < R) {
+          frag[(2 * k) * R + a] = D2_0;
+          frag[(2 * k + 1) * R + a] = D2_1;
         }
-        __syncwarp();
-        if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_addr(&ring.empty[st])) : "memory");
+        if (threadIdx.x == 0) { sMeta[2 * slot] = J; sMeta[2 * slot + 1] = g0; }
         ++c;
+        if (slot == SYM_WIN - 1 || p0 + g + 1 == lin1) {
+          __syncwarp();
+          asm volatile("bar.sync 1, %0;" ::"n"(NCW * 32) : "memory");
+          for (int q = threadIdx.x; q < (slot + 1) * 8 * R; q += NCW * 32) {
+            const int sl = q / (8 * R), rem = q - sl * 8 * R;
+            const int Jm = sMeta[2 * sl], g0m = sMeta[2 * sl + 1];
+            if (g0m + rem / R < N) {
+              double sum = 0.0;
+#pragma unroll
+              for (int w = 0; w < NCW; ++w) sum += sAcc[(size_t)((w * SYM_WIN + sl) * 8) * R + rem];
+              kp.dense_t2[(size_t)Jm * R * N + (size_t)g0m * R + rem] = sum;
+            }
+          }
+          __syncwarp();
+          asm volatile("bar.sync 1, %0;" ::"n"(NCW * 32) : "memory");
+        }
       }
+      lin = p0 + gb;
+      // direct partials of this (CTA, segment) run: every column of the segment, zeros included
       if (a < R && !(dbg & 8)) {
+        double *part = kp.dense_part + (size_t)(blockIdx.x - ld_const(kp.sym_cfirst + J)) * R * N;
 #pragma unroll
         for (int t = 0; t < 4; ++t) {
           const int col = cw0 + 8 * t + 2 * k;
-          if (col >= gmin && col < N) part[(size_t)col * R + a] = D1[t][0];
-          if (col + 1 >= gmin && col + 1 < N) part[(size_t)(col + 1) * R + a] = D1[t][1];
+          if (col < N) part[(size_t)col * R + a] = D1[t][0];
+          if (col + 1 < N) part[(size_t)(col + 1) * R + a] = D1[t][1];
         }
       }
     }
   }
-  if (!(dbg & 2)) ring.count += total;
+  if (!(dbg & 2)) ring.count += (unsigned)(lin1 - lin0);
   __syncthreads();
-  // transposed results: fixed-order sum over the consumer warps
-  if (!(dbg & 16)) {
-    for (int q = threadIdx.x; q < ng * 8 * R; q += blockDim.x) {
-      const int gi = q / (8 * R), rem = q - gi * 8 * R, rr = rem / R, a = rem - rr * R;
-      const int row = sG[gi] + rr;
-      if (row < N) {
-        double sum = 0.0;
-        for (int w = 0; w < NCW; ++w) sum += sAcc2[((size_t)(w * ng + gi) * 8 + rr) * R + a];
-        kp.dense_t2[(size_t)row * R + a] = sum;
-      }
-    }
-  }
-}
-
-template <int R, int DH>
-__device__ void phase_pz_old(const KParams &kp, int cb, const double *V, double *Zout, double (&acc)[NRED]) {
-  constexpr int TS = R * DH;
-  const double *X = kp.v[V_X0 + cb];
-  const bool symm = kp.sym_ok != 0;
-  const int nslabs_full = (kp.N + kp.dense_per - 1) / kp.dense_per;
-  const size_t stride = (size_t)R * kp.N;
-  RowIter<R> it(kp);
-  const bool valid = (it.a < R) && (it.c < DH);
-  const int e = it.c * R + it.a;
-  for (int jb = it.jb; jb < it.r1; jb += it.stride) {
-    const int j = jb + it.sgw;
-    const bool act = (j < it.r1);
-    const int js = act ? j : it.r1 - 1;
-    const bool ld = act && valid;
-    const size_t idx = (size_t)js * TS + e;
-    const double x = ld ? __ldcg(X + idx) : 0.0;
-    double t = 0.0;
-    if (ld) {
-      const double *pp = kp.dense_part + idx;
-      // symmetric variant: column col = js*DH + c receives direct partials from the CTAs whose first row group
-      // starts at or before it (the host deals group b to CTA b first, so these are CTAs 0 .. col/8), plus the
-      // transposed result of its own row
-      const int nslabs = symm ? min(kp.grid, (js * DH + it.c) / 8 + 1) : nslabs_full;
-      if (symm) t = __ldcg(kp.dense_t2 + idx);
-      int b = 0;
-      // fixed summation order (slab 0, 1, 2, ...) with 16 independent L2 loads in flight per lane
-      for (; b + 16 <= nslabs; b += 16) {
-        double tt[16];
-#pragma unroll
-        for (int u = 0; u < 16; ++u) tt[u] = __ldcg(pp + (size_t)(b + u) * stride);
-#pragma unroll
-        for (int u = 0; u < 16; ++u) t += tt[u];
-      }
-      for (; b + 4 <= nslabs; b += 4) {
-        const double t0 = __ldcg(pp + (size_t)b * stride), t1 = __ldcg(pp + (size_t)(b + 1) * stride);
-        const double t2 = __ldcg(pp + (size_t)(b + 2) * stride), t3 = __ldcg(pp + (size_t)(b + 3) * stride);
-        t += t0; t += t1; t += t2; t += t3;
-      }
-      for (; b < nslabs; ++b) t += __ldcg(pp + (size_t)b * stride);
-    }
-    double ya[3], sym[3];
-    const double z = tangent_project_elem<R, DH>(x, t, it.a, it.c, ya, sym);
-    if (ld) {
-      Zout[idx] = z;
-      acc[0] = fma(z, __ldcg(V + idx), acc[0]);
-    }
-  }
 }
 
 // Sum of the partial panels + tangent projection.  Step 1 is a flat job over the CTA's contiguous element range
@@ -614,6 +582,7 @@ template <int R, int DH>
 __device__ void phase_pz(const KParams &kp, int cb, const double *V, double *Zout, double *sT, double (&acc)[NRED]) {
   constexpr int TS = R * DH;
   constexpr int PZ_TILE = DENSE_PER_MAX * R;          // elements staged per round (sT = the V staging area of the dense phases)
+  const int nseg_sym = (kp.N + SYM_SEG - 1) / SYM_SEG;
   const double *X = kp.v[V_X0 + cb];
   const bool symm = kp.sym_ok != 0;
   const int nslabs_full = (kp.N + kp.dense_per - 1) / kp.dense_per;
@@ -632,27 +601,25 @@ __device__ void phase_pz(const KParams &kp, int cb, const double *V, double *Zou
       const int part = q / E, el = q - part * E;
       const size_t idx = base + el;
       const int col = (int)(idx / R);
-      const int nslabs = symm ? min(kp.grid, col / 8 + 1) : nslabs_full;
-      // this part's slab range [b0, b1): contiguous, so the overall order stays slab 0, 1, 2, ...
+      // symmetric variant: ccount[J] direct panels of the column's segment J, then the transposed slots of the
+      // segments J(row group) .. nseg-1; one virtual list so that the parts split it evenly
+      const int J = col / SYM_SEG;
+      const int ndir = symm ? ld_const(kp.sym_ccount + J) : nslabs_full;
+      const int jt0 = (col & ~7) / SYM_SEG;
+      const int nslabs = symm ? ndir + (nseg_sym - jt0) : nslabs_full;
       const int b0 = (int)((long long)nslabs * part / P), b1 = (int)((long long)nslabs * (part + 1) / P);
       const double *pp = kp.dense_part + idx;
-      double t = (symm && part == 0) ? __ldcg(kp.dense_t2 + idx) : 0.0;
-      int b = b0;
-      for (; b + 32 <= b1; b += 32) {
+      // slot b >= ndir is segment jt0 + b - ndir of the transposed partials
+      const double *pt = symm ? kp.dense_t2 + idx + (ptrdiff_t)(jt0 - ndir) * (ptrdiff_t)stride : pp;
+      double t = 0.0;
+      for (int b = b0; b < b1; b += 32) {                                     // 32 independent L2 loads in flight, summed in order
         double tt[32];
 #pragma unroll
-        for (int u = 0; u < 32; ++u) tt[u] = __ldcg(pp + (size_t)(b + u) * stride);
+        for (int u = 0; u < 32; ++u)
+          tt[u] = (b + u < b1) ? __ldcg(((b + u) < ndir ? pp : pt) + (size_t)(b + u) * stride) : 0.0;
 #pragma unroll
         for (int u = 0; u < 32; ++u) t += tt[u];
       }
-      for (; b + 8 <= b1; b += 8) {
-        double tt[8];
-#pragma unroll
-        for (int u = 0; u < 8; ++u) tt[u] = __ldcg(pp + (size_t)(b + u) * stride);
-#pragma unroll
-        for (int u = 0; u < 8; ++u) t += tt[u];
-      }
-      for (; b < b1; ++b) t += __ldcg(pp + (size_t)b * stride);
       sT[q] = t;
     }
     __syncthreads();
@@ -765,7 +732,7 @@ template <int R, int DH> __global__ void __launch_bounds__(OPT_THREADS, 1) k_opt
   ring.full = reinterpret_cast<uint64_t *>(ring.buf + (size_t)DENSE_RING_DOUBLES);
   ring.empty = ring.full + DENSE_NST;
   ring.count = 0;
-  double *sAcc2 = reinterpret_cast<double *>(ring.empty + DENSE_NST);   // symmetric variant: 15 x SYM_MAXG x 8 x R
+  int *sMeta = reinterpret_cast<int *>(ring.empty + DENSE_NST);         // symmetric variant: (segment, first row) per window slot
   // bulk-TMA streaming needs 16-byte aligned rows (N even) and only pays off for a real stream
   const bool dense_tma = (kp.pinv != nullptr) && ((kp.N & 1) == 0) && (kp.N >= 2048);
   const bool dense_sym = dense_tma && (kp.sym_ok != 0);
@@ -816,7 +783,7 @@ template <int R, int DH> __global__ void __launch_bounds__(OPT_THREADS, 1) k_opt
   }
   if (kp.op == OP_PRECON) {
     if (precond == DPGO_PRECOND_DENSE_EXACT) {
-      if (dense_sym) phase_dense_sym<R>(kp, kp.v[V_AUX], sV, ring, sAcc2);
+      if (dense_sym) phase_dense_sym<R>(kp, kp.v[V_AUX], ring, sV, sMeta);
       else if (dense_tma) phase_dense_tma<R>(kp, kp.v[V_AUX], sV, ring);
       else phase_dense<R>(kp, kp.v[V_AUX], sV);
       zero(acc); phase_end<0>(kp, bc, acc);
@@ -908,14 +875,12 @@ template <int R, int DH> __global__ void __launch_bounds__(OPT_THREADS, 1) k_opt
     while (true) {
       // -- z0 = M^-1 g for the dense preconditioner (pose-local ones were fused into phase E)
       if (!z0_valid) {
-        if (dense_sym) phase_dense_sym<R>(kp, kp.v[V_RG0 + cb], sV, ring, sAcc2);
+        if (dense_sym) phase_dense_sym<R>(kp, kp.v[V_RG0 + cb], ring, sV, sMeta);
         else if (dense_tma) phase_dense_tma<R>(kp, kp.v[V_RG0 + cb], sV, ring);
         else phase_dense<R>(kp, kp.v[V_RG0 + cb], sV);
         zero(acc); phase_end<0>(kp, bc, acc);
         tick(1);
-        zero(acc);
-        if (kp.dbg & 64) phase_pz_old<R, DH>(kp, cb, kp.v[V_RG0 + cb], kp.v[V_Z00 + cb], acc);
-        else phase_pz<R, DH>(kp, cb, kp.v[V_RG0 + cb], kp.v[V_Z00 + cb], sV, acc);
+        zero(acc); phase_pz<R, DH>(kp, cb, kp.v[V_RG0 + cb], kp.v[V_Z00 + cb], sV, acc);
         phase_end<1>(kp, bc, acc);
         tick(2);
         zr0 = acc[0];
@@ -963,14 +928,12 @@ template <int R, int DH> __global__ void __launch_bounds__(OPT_THREADS, 1) k_opt
         }
         double zr_new = acc[1];
         if (precond == DPGO_PRECOND_DENSE_EXACT) {
-          if (dense_sym) phase_dense_sym<R>(kp, kp.v[V_RES], sV, ring, sAcc2);
+          if (dense_sym) phase_dense_sym<R>(kp, kp.v[V_RES], ring, sV, sMeta);
           else if (dense_tma) phase_dense_tma<R>(kp, kp.v[V_RES], sV, ring);
           else phase_dense<R>(kp, kp.v[V_RES], sV);
           zero(acc); phase_end<0>(kp, bc, acc);
           tick(1);
-          zero(acc);
-          if (kp.dbg & 64) phase_pz_old<R, DH>(kp, cb, kp.v[V_RES], kp.v[V_Z], acc);
-          else phase_pz<R, DH>(kp, cb, kp.v[V_RES], kp.v[V_Z], sV, acc);
+          zero(acc); phase_pz<R, DH>(kp, cb, kp.v[V_RES], kp.v[V_Z], sV, acc);
           phase_end<1>(kp, bc, acc);
           tick(2);
           zr_new = acc[0];
@@ -1188,7 +1151,7 @@ __global__ void k_build_G(int nposes, const int *__restrict__ pose_ids, const in
 // launchers
 // ---------------------------------------------------------------------------------------------
 template <int R, int DH> static cudaError_t launch_optimize_t(const KParams &kp, cudaStream_t stream) {
-  const size_t smem = ((OPT_THREADS / 32) * NRED + NRED + (size_t)DENSE_PER_MAX * R + (size_t)DENSE_RING_DOUBLES + 2 * DENSE_NST + (size_t)(OPT_THREADS / 32 - 1) * 16 * 8 * R) * sizeof(double);
+  const size_t smem = ((OPT_THREADS / 32) * NRED + NRED + (size_t)DENSE_PER_MAX * R + (size_t)DENSE_RING_DOUBLES + 2 * DENSE_NST + (size_t)SYM_META_DOUBLES) * sizeof(double);
   static bool attr_set[64] = {};
   int dev = 0;
   cudaGetDevice(&dev);
@@ -1202,7 +1165,7 @@ template <int R, int DH> static cudaError_t launch_optimize_t(const KParams &kp,
 }
 
 template <int R, int DH> static int max_grid_t(int device) {
-  const size_t smem = ((OPT_THREADS / 32) * NRED + NRED + (size_t)DENSE_PER_MAX * R + (size_t)DENSE_RING_DOUBLES + 2 * DENSE_NST + (size_t)(OPT_THREADS / 32 - 1) * 16 * 8 * R) * sizeof(double);
+  const size_t smem = ((OPT_THREADS / 32) * NRED + NRED + (size_t)DENSE_PER_MAX * R + (size_t)DENSE_RING_DOUBLES + 2 * DENSE_NST + (size_t)SYM_META_DOUBLES) * sizeof(double);
   cudaFuncSetAttribute(k_optimize<R, DH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   int per_sm = 0, sms = 0;
   if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_optimize<R, DH>, OPT_THREADS, smem) != cudaSuccess) return 0;

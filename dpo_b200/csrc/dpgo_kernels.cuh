@@ -48,9 +48,11 @@ struct KParams {
   double *dense_part;    // grid * r * N  per-CTA partial products of the dense preconditioner
   int dense_per;         // rows of pinv per CTA
   int sym_ok;            // symmetric (upper-triangle) variant of the dense preconditioner is planned
-  const int *sym_ptr;    // grid+1: per-CTA range into sym_g0
-  const int *sym_g0;     // first row of each 8-row group, per CTA ascending
-  double *dense_t2;      // r x N transposed-product results
+  const int *sym_cut;    // grid+1: per-CTA range of chunk indices (segment-major order of (segment, 8-row group))
+  const int *sym_segptr; // nseg+1: first chunk index of every column segment
+  const int *sym_cfirst; // nseg: first CTA that touches the segment
+  const int *sym_ccount; // nseg: number of (consecutive) CTAs that touch it = partial panels of its columns
+  double *dense_t2;      // nseg x r x N transposed-product partials, slot = column segment
   const int *cta_rows;   // grid+1 balanced row partition
   const double *G;       // linear term r x N
   double *v[V_COUNT];
