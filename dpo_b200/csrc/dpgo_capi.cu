@@ -56,6 +56,8 @@ struct dpgo_problem {
   double *d_bval = nullptr, *d_dinv = nullptr, *d_pinv = nullptr, *d_dense_part = nullptr, *d_dense_t2 = nullptr;
   int dense_per = 1;
   int sym_ok = 0;                // symmetric (upper-triangle) dense preconditioner planned
+  double *d_ppack = nullptr;
+  long long *d_sym_off = nullptr;
   int *d_sym_cut = nullptr, *d_sym_segptr = nullptr, *d_sym_cfirst = nullptr, *d_sym_ccount = nullptr;
   // vectors
   double *d_G = nullptr;
@@ -93,6 +95,8 @@ void fill_kparams(const dpgo_problem *p, dpgo::KParams &kp, int op, const dpgo_o
   kp.dense_part = p->d_dense_part;
   kp.dense_per = p->dense_per;
   kp.sym_ok = p->sym_ok;
+  kp.ppack = p->d_ppack;
+  kp.sym_off = p->d_sym_off;
   kp.sym_cut = p->d_sym_cut;
   kp.sym_segptr = p->d_sym_segptr;
   kp.sym_cfirst = p->d_sym_cfirst;
@@ -159,11 +163,16 @@ int ensure_dense(dpgo_problem *p) {
     }
     const int nchunks = segptr[(size_t)nseg];
     std::vector<double> cum((size_t)nchunks + 1, 0.0);
+    std::vector<long long> off((size_t)nchunks + 1, 0);      // chunk-major packed layout: 8 rows x (width up to 8, + 4) doubles
     {
       int lin = 0;
       for (int J = 0; J < nseg; ++J) {
         const int s0 = J * SEG, s1 = (int)std::min<int64_t>(N, (int64_t)s0 + SEG);
-        for (int g = 0; 8 * g < s1; ++g, ++lin) cum[(size_t)lin + 1] = cum[(size_t)lin] + (double)(s1 - std::max(s0, 8 * g)) + 48.0;
+        for (int g = 0; 8 * g < s1; ++g, ++lin) {
+          const int width = s1 - std::max(s0, 8 * g);
+          cum[(size_t)lin + 1] = cum[(size_t)lin] + (double)width + 48.0;
+          off[(size_t)lin + 1] = off[(size_t)lin] + 8LL * (((width + 7) & ~7) + 4);
+        }
       }
     }
     std::vector<int> cut((size_t)G + 1, 0);
@@ -198,10 +207,15 @@ int ensure_dense(dpgo_problem *p) {
       DPGO_CUDA(cudaMalloc(&p->d_sym_ccount, sizeof(int) * ccount.size()));
       DPGO_CUDA(cudaMalloc(&p->d_dense_t2, sizeof(double) * (size_t)nseg * p->r * N));
       DPGO_CUDA(cudaMemset(p->d_dense_t2, 0, sizeof(double) * (size_t)nseg * p->r * N));
+      DPGO_CUDA(cudaMalloc(&p->d_sym_off, sizeof(long long) * off.size()));
+      DPGO_CUDA(cudaMalloc(&p->d_ppack, sizeof(double) * (size_t)off[(size_t)nchunks]));
+      DPGO_CUDA(cudaMemcpy(p->d_sym_off, off.data(), sizeof(long long) * off.size(), cudaMemcpyHostToDevice));
       DPGO_CUDA(cudaMemcpy(p->d_sym_cut, cut.data(), sizeof(int) * cut.size(), cudaMemcpyHostToDevice));
       DPGO_CUDA(cudaMemcpy(p->d_sym_segptr, segptr.data(), sizeof(int) * segptr.size(), cudaMemcpyHostToDevice));
       DPGO_CUDA(cudaMemcpy(p->d_sym_cfirst, cfirst.data(), sizeof(int) * cfirst.size(), cudaMemcpyHostToDevice));
       DPGO_CUDA(cudaMemcpy(p->d_sym_ccount, ccount.data(), sizeof(int) * ccount.size(), cudaMemcpyHostToDevice));
+      DPGO_CUDA(dpgo::launch_pack_sym(p->d_pinv, (int)N, nchunks, p->d_sym_segptr, nseg, p->d_sym_off, p->d_ppack, p->stream));
+      DPGO_CUDA(cudaStreamSynchronize(p->stream));
       p->sym_ok = 1;
     }
   }
@@ -313,7 +327,7 @@ int build_from_triplets(dpgo_problem *p, std::vector<BlockTriplet> &trip, unsign
   cudaSetDevice(p->device);
   free_dev(p->d_rowptr); free_dev(p->d_bcol); free_dev(p->d_bval); free_dev(p->d_dinv); free_dev(p->d_pinv);
   free_dev(p->d_cta_rows); free_dev(p->d_partials); free_dev(p->d_dense_part); free_dev(p->d_groups);
-  free_dev(p->d_dense_t2); free_dev(p->d_sym_cut); free_dev(p->d_sym_segptr); free_dev(p->d_sym_cfirst); free_dev(p->d_sym_ccount);
+  free_dev(p->d_dense_t2); free_dev(p->d_ppack); free_dev(p->d_sym_off); free_dev(p->d_sym_cut); free_dev(p->d_sym_segptr); free_dev(p->d_sym_cfirst); free_dev(p->d_sym_ccount);
   p->sym_ok = 0;
   p->have_Q = false;
   p->ngroups = 0;
@@ -480,7 +494,7 @@ int dpgo_problem_destroy(dpgo_problem_t *p) {
   if (p->stream) cudaStreamSynchronize(p->stream);
   free_dev(p->d_rowptr); free_dev(p->d_bcol); free_dev(p->d_cta_rows); free_dev(p->d_bval); free_dev(p->d_groups);
   free_dev(p->d_dinv); free_dev(p->d_pinv); free_dev(p->d_dense_part); free_dev(p->d_G);
-  free_dev(p->d_dense_t2); free_dev(p->d_sym_cut); free_dev(p->d_sym_segptr); free_dev(p->d_sym_cfirst); free_dev(p->d_sym_ccount);
+  free_dev(p->d_dense_t2); free_dev(p->d_ppack); free_dev(p->d_sym_off); free_dev(p->d_sym_cut); free_dev(p->d_sym_segptr); free_dev(p->d_sym_cfirst); free_dev(p->d_sym_ccount);
   for (int i = 0; i < dpgo::V_COUNT; ++i) free_dev(p->d_vec[i]);
   free_dev(p->d_S[0]); free_dev(p->d_S[1]); free_dev(p->d_partials); free_dev(p->d_bar); free_dev(p->d_phase_ns); free_dev(p->d_result);
   free_dev(p->d_public); free_dev(p->d_pose_ids); free_dev(p->d_pose_ptr); free_dev(p->d_edge_slot);

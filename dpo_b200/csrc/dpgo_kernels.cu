@@ -326,6 +326,20 @@ __device__ __forceinline__ void mbar_wait_parity(uint64_t *bar, unsigned parity)
       : "memory");
 }
 
+__device__ __forceinline__ void mbar_wait_parity_s(uint32_t bar_s, unsigned parity) {   // same, 32-bit shared address
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "DWS_LOOP:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DWS_DONE;\n"
+      "bra DWS_LOOP;\n"
+      "DWS_DONE:\n"
+      "}\n" ::"r"(bar_s),
+      "r"(parity)
+      : "memory");
+}
+
 template <int R> __device__ void phase_dense_tma(const KParams &kp, const double *V, double *sV, DenseRing &ring) {
   const int N = kp.N;
   const int per = kp.dense_per;
@@ -415,9 +429,11 @@ template <int R> __device__ void phase_dense_tma(const KParams &kp, const double
 //   * direct partials: one panel slot per (CTA, segment) -- ~grid/nseg+1 slots per column instead of `grid`;
 //   * transposed results: chunk (J, g) is owned by exactly one CTA, which writes rows 8g..8g+7 of slot J of dense_t2.
 // phase_pz adds, per element, the <= ccount[J] panel slots and the <= nseg transposed slots in fixed order.
-// Warp 15 is the producer (bulk TMA: 8 row pieces + the 8 V columns of the group per chunk, L2 evict-first for the
+// The upper triangle is stored chunk-major (ppack: a chunk's 8 rows x (width rounded up to 8, + 4 pad) doubles are
+// contiguous, chunks in processing order), so a CTA's whole run is ONE contiguous byte range of HBM.
+// Warp 15 is the producer (bulk TMA: one copy per chunk + the 8 V columns of the group, L2 evict-first for the
 // matrix), warps 0..14 consume through full/empty mbarriers; the consumers park their transposed fragments in shared
-// memory and meet at a named barrier once per SYM_WIN chunks to sum them over the warps.
+// memory and meet at a named barrier once per SYM_WIN/2 chunks; the sum over the warps overlaps the next chunks.
 constexpr int SYM_NST = 5;
 constexpr int SYM_SEG = (OPT_THREADS / 32 - 1) * 32;   // 480 columns per segment: 32 per consumer warp
 constexpr int SYM_SROW = SYM_SEG + 4;                   // staged row pitch: 3872 B = 32 mod 128 (conflict-light tile reads)
@@ -439,41 +455,37 @@ template <int R> __device__ void phase_dense_sym(const KParams &kp, const double
   const int lin0 = ld_const(kp.sym_cut + blockIdx.x), lin1 = ld_const(kp.sym_cut + blockIdx.x + 1);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   constexpr int NCW = OPT_THREADS / 32 - 1;             // consumer warps
-  const int dbg = kp.dbg;
   int J0 = 0;
   while (J0 + 1 < nseg && ld_const(kp.sym_segptr + J0 + 1) <= lin0) ++J0;
   if (warp == NCW) {
     // ---------------- producer ----------------
-    if (lane == 0 && !(dbg & 2)) {
+    if (lane == 0) {
       uint64_t pol;
       asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
       unsigned c = ring.count;
       int lin = lin0;
       for (int J = J0; J < nseg && lin < lin1; ++J) {
-        const int s0 = J * SYM_SEG, s1 = min(N, s0 + SYM_SEG);
         const int p0 = ld_const(kp.sym_segptr + J), p1 = ld_const(kp.sym_segptr + J + 1);
         const int gb = min(p1, lin1) - p0;
         for (int g = lin - p0; g < gb; ++g) {
           const int g0 = 8 * g;
-          const int col_lo = max(s0, g0);
-          const unsigned rowbytes = (unsigned)(s1 - col_lo) * 8u;
           const int nrows = min(8, N - g0);
           const unsigned vbytes = (unsigned)(nrows * R) * 8u;
+          const long long o0 = __ldg(kp.sym_off + p0 + g), o1 = __ldg(kp.sym_off + p0 + g + 1);
+          const unsigned cbytes = (unsigned)(o1 - o0) * 8u;
           const int st = c % SYM_NST;
           if (c >= SYM_NST) mbar_wait_parity(&ring.empty[st], ((c / SYM_NST) - 1) & 1);
           double *stage = ring.buf + (size_t)st * SYM_STAGE;
-          asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(&ring.full[st])),
-                       "r"(rowbytes * (unsigned)nrows + vbytes)
+          asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(&ring.full[st])), "r"(cbytes + vbytes)
                        : "memory");
           asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
                            smem_addr(stage + SYM_VOFF)),
                        "l"(V + (size_t)g0 * R), "r"(vbytes), "r"(smem_addr(&ring.full[st]))
                        : "memory");
-          for (int rr = 0; rr < nrows; ++rr)
-            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(
-                             smem_addr(stage + (size_t)rr * SYM_SROW)),
-                         "l"(kp.pinv + (size_t)(g0 + rr) * N + col_lo), "r"(rowbytes), "r"(smem_addr(&ring.full[st])), "l"(pol)
-                         : "memory");
+          asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(
+                           smem_addr(stage)),
+                       "l"(kp.ppack + o0), "r"(cbytes), "r"(smem_addr(&ring.full[st])), "l"(pol)
+                       : "memory");
           ++c;
         }
         lin = p0 + gb;
@@ -483,14 +495,23 @@ template <int R> __device__ void phase_dense_sym(const KParams &kp, const double
     // ---------------- consumers ----------------
     const int a = lane >> 2, k = lane & 3;                // A fragment: row a, column k ; D fragment: row a, columns 2k, 2k+1
     const int bn = lane >> 2, bk = lane & 3;              // B fragment: column n = lane>>2, row k = lane&3
-    unsigned c = ring.count;
-    const unsigned c_begin = c;
+    const int ac = min(a, R - 1);                         // rows a >= R of the fragments are never stored: any finite operand will do
+    // lane-constant offsets (doubles) of the interior path: full-width chunk, every tile right of the diagonal
+    const int offD = bk * SYM_SROW + 32 * warp + bn;      // direct      B[kk][n] = P[g0 + kk][ctile + n]
+    const int offT = bn * SYM_SROW + 32 * warp + bk;      // transposed  B[c'][n] = P[g0 + n][ctile + c']
+    const int offV = SYM_VOFF + k * R + ac;               // V[a, g0 + k]
+    double *fragLane = sAcc + (size_t)(warp * SYM_WIN * 8 + 2 * k) * R + ac;
+    const uint32_t full_s = smem_addr(ring.full), empty_s = smem_addr(ring.empty);
+    int st = (int)(ring.count % SYM_NST);
+    unsigned ph = (ring.count / SYM_NST) & 1u;
+    int cidx = 0;                                         // chunks done in this phase
     int lin = lin0;
     for (int J = J0; J < nseg && lin < lin1; ++J) {
       const int s0 = J * SYM_SEG, s1 = min(N, s0 + SYM_SEG);
       const int p0 = ld_const(kp.sym_segptr + J), p1 = ld_const(kp.sym_segptr + J + 1);
       const int gb = min(p1, lin1) - p0;
       const int cw0 = s0 + 32 * warp;
+      const bool fullseg = (s1 - s0 == SYM_SEG);
       double va[4][2];                                    // transposed-product A operands: V[a, ctile + 4q + k]
 #pragma unroll
       for (int t = 0; t < 4; ++t)
@@ -505,47 +526,67 @@ template <int R> __device__ void phase_dense_sym(const KParams &kp, const double
       for (int g = lin - p0; g < gb; ++g) {
         const int g0 = 8 * g;
         double D2_0 = 0.0, D2_1 = 0.0;
-        if (!(dbg & 2)) {
+        mbar_wait_parity_s(full_s + 8u * (unsigned)st, ph);
+        const double *base = ring.buf + (size_t)st * SYM_STAGE;
+        if (fullseg && g0 + 8 <= s0) {
+          // interior chunk (>90 % of the bytes): no masks, constant pitch
+          const double a1_0 = base[offV], a1_1 = base[offV + 4 * R];
+          const double *bD = base + offD, *bT = base + offT;
+          double E2_0 = 0.0, E2_1 = 0.0;                       // second transposed chain: halves the dependent DMMA depth
+#pragma unroll
+          for (int t = 0; t < 4; ++t) {
+            dmma884(D1[t][0], D1[t][1], a1_0, bD[8 * t]);
+            dmma884(D1[t][0], D1[t][1], a1_1, bD[4 * SYM_SROW + 8 * t]);
+            if (t & 1) {
+              dmma884(E2_0, E2_1, va[t][0], bT[8 * t]);
+              dmma884(E2_0, E2_1, va[t][1], bT[8 * t + 4]);
+            } else {
+              dmma884(D2_0, D2_1, va[t][0], bT[8 * t]);
+              dmma884(D2_0, D2_1, va[t][1], bT[8 * t + 4]);
+            }
+          }
+          D2_0 += E2_0;
+          D2_1 += E2_1;
+        } else {
+          // diagonal / ragged chunk: tiles left of the diagonal or past the segment end are skipped (warp-uniform)
           const int col_lo = max(s0, g0);
-          const int st = c % SYM_NST;
-          mbar_wait_parity(&ring.full[st], (c / SYM_NST) & 1);
-          const double *base = ring.buf + (size_t)st * SYM_STAGE;
+          const int pitch = ((s1 - col_lo + 7) & ~7) + 4;     // chunk row pitch in ppack (= 32 or 96 bytes mod 128)
           const double a1_0 = (a < R && g0 + k < N) ? base[SYM_VOFF + k * R + a] : 0.0;            // V[a, g0 + k]
           const double a1_1 = (a < R && g0 + 4 + k < N) ? base[SYM_VOFF + (4 + k) * R + a] : 0.0;  // V[a, g0 + 4 + k]
 #pragma unroll
           for (int t = 0; t < 4; ++t) {
             const int ctile = cw0 + 8 * t;
-            if (dbg & 1) continue;
-            if (ctile < g0 || ctile >= s1) continue;         // warp-uniform: left of the diagonal / past the segment
+            if (ctile < g0 || ctile >= s1) continue;
             const int x = ctile - col_lo;
-            // direct: B[kk][n] = P[g0 + 4q + kk][ctile + n]
-            dmma884(D1[t][0], D1[t][1], a1_0, base[(size_t)bk * SYM_SROW + x + bn]);
-            dmma884(D1[t][0], D1[t][1], a1_1, base[(size_t)(4 + bk) * SYM_SROW + x + bn]);
+            dmma884(D1[t][0], D1[t][1], a1_0, base[bk * pitch + x + bn]);
+            dmma884(D1[t][0], D1[t][1], a1_1, base[(4 + bk) * pitch + x + bn]);
             if (ctile > g0) {
-              // transposed: B[c'][n] = P[g0 + n][ctile + 4q + c']
-              dmma884(D2_0, D2_1, va[t][0], base[(size_t)bn * SYM_SROW + x + bk]);
-              dmma884(D2_0, D2_1, va[t][1], base[(size_t)bn * SYM_SROW + x + 4 + bk]);
+              dmma884(D2_0, D2_1, va[t][0], base[bn * pitch + x + bk]);
+              dmma884(D2_0, D2_1, va[t][1], base[bn * pitch + x + 4 + bk]);
             }
           }
-          __syncwarp();
-          if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_addr(&ring.empty[st])) : "memory");
         }
+        __syncwarp();
+        if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(empty_s + 8u * (unsigned)st) : "memory");
+        if (++st == SYM_NST) { st = 0; ph ^= 1u; }
         // transposed result of this chunk: rows g0 + 2k, g0 + 2k + 1 (fragment columns), component a.  The fragments of
-        // SYM_WIN consecutive chunks are parked per warp in shared memory; every SYM_WIN chunks (and after the CTA's
-        // last chunk) the consumers meet and sum them over the warps in fixed order: 2 named barriers per window.
-        const int slot = (int)(c - c_begin) % SYM_WIN;
-        double *frag = sAcc + (size_t)((warp * SYM_WIN + slot) * 8) * R;
+        // SYM_WIN consecutive chunks are parked per warp in shared memory (two halves used alternately).
+        const int slot = cidx & (SYM_WIN - 1);
         if (a < R) {
-          frag[(2 * k) * R + a] = D2_0;
-          frag[(2 * k + 1) * R + a] = D2_1;
+          fragLane[slot * 8 * R] = D2_0;
+          fragLane[slot * 8 * R + R] = D2_1;
         }
         if (threadIdx.x == 0) { sMeta[2 * slot] = J; sMeta[2 * slot + 1] = g0; }
-        ++c;
-        if (slot == SYM_WIN - 1 || p0 + g + 1 == lin1) {
+        ++cidx;
+        if ((slot & (SYM_WIN / 2 - 1)) == SYM_WIN / 2 - 1 || p0 + g + 1 == lin1) {
+          // one half of the window is complete: the warps meet, then up to 160 threads sum it while the others go on
+          // filling the other half.  One barrier per half window: a half is rewritten only after the NEXT barrier, which
+          // the summing threads reach after they are done with it.
           __syncwarp();
           asm volatile("bar.sync 1, %0;" ::"n"(NCW * 32) : "memory");
-          for (int q = threadIdx.x; q < (slot + 1) * 8 * R; q += NCW * 32) {
-            const int sl = q / (8 * R), rem = q - sl * 8 * R;
+          const int h0 = slot & (SYM_WIN / 2), nsl = (slot & (SYM_WIN / 2 - 1)) + 1;
+          for (int q = threadIdx.x; q < nsl * 8 * R; q += NCW * 32) {
+            const int sl = h0 + q / (8 * R), rem = q % (8 * R);
             const int Jm = sMeta[2 * sl], g0m = sMeta[2 * sl + 1];
             if (g0m + rem / R < N) {
               double sum = 0.0;
@@ -554,13 +595,11 @@ template <int R> __device__ void phase_dense_sym(const KParams &kp, const double
               kp.dense_t2[(size_t)Jm * R * N + (size_t)g0m * R + rem] = sum;
             }
           }
-          __syncwarp();
-          asm volatile("bar.sync 1, %0;" ::"n"(NCW * 32) : "memory");
         }
       }
       lin = p0 + gb;
       // direct partials of this (CTA, segment) run: every column of the segment, zeros included
-      if (a < R && !(dbg & 8)) {
+      if (a < R) {
         double *part = kp.dense_part + (size_t)(blockIdx.x - ld_const(kp.sym_cfirst + J)) * R * N;
 #pragma unroll
         for (int t = 0; t < 4; ++t) {
@@ -571,7 +610,7 @@ template <int R> __device__ void phase_dense_sym(const KParams &kp, const double
       }
     }
   }
-  if (!(dbg & 2)) ring.count += (unsigned)(lin1 - lin0);
+  ring.count += (unsigned)(lin1 - lin0);
   __syncthreads();
 }
 
@@ -753,14 +792,18 @@ template <int R, int DH> __global__ void __launch_bounds__(OPT_THREADS, 1) k_opt
   bc.parity = 0;
   // diagnostic phase clock: CTA 0 / thread 0 charges the time since the previous tick to a phase kind
   // (0 eval, 1 dense apply, 2 partial sums + projection, 3 Hessian product, 4 tCG update, 5 retraction, 6 final)
+  // slot 7 accumulates SM cycles (clock64) over the same intervals: cycles / ns = the SM clock the kernel really ran at
   unsigned long long tick_last = 0;
+  long long tick_clk = 0;
   const bool ticking = (kp.phase_ns != nullptr) && blockIdx.x == 0 && threadIdx.x == 0;
   auto tick = [&](int kind) {
     if (ticking) {
       unsigned long long t;
       asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-      if (kind >= 0) kp.phase_ns[kind] += t - tick_last;
+      const long long ck = clock64();
+      if (kind >= 0) { kp.phase_ns[kind] += t - tick_last; kp.phase_ns[7] += (unsigned long long)(ck - tick_clk); }
       tick_last = t;
+      tick_clk = ck;
     }
   };
   tick(-1);
@@ -1253,9 +1296,33 @@ __global__ void k_bsr_to_dense(int n, int dh, int64_t nb, const int *__restrict_
   const int j = lo, i = bcol[b];
   A[(size_t)(dh * i + k) + (size_t)N * (dh * j + c)] = bval[t];
 }
+// one block per chunk: copy the 8 x width piece of the dense inverse into its padded chunk-major slot (zero fill)
+__global__ void k_pack_sym(const double *__restrict__ pinv, int N, int nchunks, const int *__restrict__ segptr, int nseg,
+                           const long long *__restrict__ off, double *__restrict__ ppack) {
+  for (int lin = blockIdx.x; lin < nchunks; lin += gridDim.x) {
+    int J = 0;
+    while (J + 1 < nseg && segptr[J + 1] <= lin) ++J;
+    const int s0 = J * SYM_SEG, s1 = min(N, s0 + SYM_SEG);
+    const int g0 = 8 * (lin - segptr[J]);
+    const int col_lo = max(s0, g0), width = s1 - col_lo;
+    const int pitch = ((width + 7) & ~7) + 4;
+    double *dst = ppack + off[lin];
+    for (int q = threadIdx.x; q < 8 * pitch; q += blockDim.x) {
+      const int rr = q / pitch, x = q - rr * pitch;
+      dst[q] = (g0 + rr < N && x < width) ? pinv[(size_t)(g0 + rr) * N + col_lo + x] : 0.0;
+    }
+  }
+}
+
 __global__ void k_add_diag(double *__restrict__ A, int N, double shift) {
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t < N) A[(size_t)t * N + t] += shift;
+}
+
+cudaError_t launch_pack_sym(const double *pinv, int N, int nchunks, const int *segptr, int nseg, const long long *off, double *ppack,
+                            cudaStream_t stream) {
+  k_pack_sym<<<std::min(nchunks, 148 * 16), 256, 0, stream>>>(pinv, N, nchunks, segptr, nseg, off, ppack);
+  return cudaGetLastError();
 }
 
 cudaError_t launch_bsr_to_dense(int n, int dh, int64_t nb, const int *rowptr, const int *bcol, const double *bval,

@@ -48,6 +48,8 @@ struct KParams {
   double *dense_part;    // grid * r * N  per-CTA partial products of the dense preconditioner
   int dense_per;         // rows of pinv per CTA
   int sym_ok;            // symmetric (upper-triangle) variant of the dense preconditioner is planned
+  const double *ppack;   // upper triangle of pinv, chunk-major: chunk = 8 rows x (padded width + 4) doubles, contiguous
+  const long long *sym_off; // nchunks+1: first double of every chunk in ppack
   const int *sym_cut;    // grid+1: per-CTA range of chunk indices (segment-major order of (segment, 8-row group))
   const int *sym_segptr; // nseg+1: first chunk index of every column segment
   const int *sym_cfirst; // nseg: first CTA that touches the segment
@@ -79,6 +81,8 @@ cudaError_t launch_pack_tiles(int ts, int count, const int *pose, const double *
 cudaError_t launch_build_G(int r, int dh, int nposes, const int *pose_ids, const int *pose_ptr, const int *edge_slot,
                            const int *edge_out, const double *edge_T, const double *edge_om, const double *gathered,
                            double *G, cudaStream_t stream);
+cudaError_t launch_pack_sym(const double *pinv, int N, int nchunks, const int *segptr, int nseg, const long long *off, double *ppack,
+                            cudaStream_t stream);
 cudaError_t launch_bsr_to_dense(int n, int dh, int64_t nb, const int *rowptr, const int *bcol, const double *bval,
                                 double shift, double *A, int N, cudaStream_t stream);
 

@@ -66,6 +66,17 @@ int main() {
   const double warps = (double)blocks * threads / 32;
   const double dmma_flops = warps * iters * 8.0 * (2.0 * 8 * 8 * 4);
   const double dfma_flops = (double)blocks * threads * iters * 8.0 * 2.0;
+  // dependent-chain sweep at the persistent kernel's occupancy (1 CTA of 512 threads per SM): DMMAs per SM per us
+  float ms_c[4] = {0, 0, 0, 0};
+  for (int rep = 0; rep < 2; ++rep) {
+    cudaEventRecord(e0); k_dmma<1><<<sms, threads>>>(out, iters); cudaEventRecord(e1); cudaEventSynchronize(e1); cudaEventElapsedTime(&ms_c[0], e0, e1);
+    cudaEventRecord(e0); k_dmma<2><<<sms, threads>>>(out, iters); cudaEventRecord(e1); cudaEventSynchronize(e1); cudaEventElapsedTime(&ms_c[1], e0, e1);
+    cudaEventRecord(e0); k_dmma<4><<<sms, threads>>>(out, iters); cudaEventRecord(e1); cudaEventSynchronize(e1); cudaEventElapsedTime(&ms_c[2], e0, e1);
+    cudaEventRecord(e0); k_dmma<8><<<sms, threads>>>(out, iters); cudaEventRecord(e1); cudaEventSynchronize(e1); cudaEventElapsedTime(&ms_c[3], e0, e1);
+  }
+  const double w1 = (double)threads / 32 * iters;   // DMMAs per SM per chain
+  printf("{\"one_cta_512\": {\"chains1\": %.1f, \"chains2\": %.1f, \"chains4\": %.1f, \"chains8\": %.1f, \"unit\": \"DMMA/SM/us\"}}\n",
+         w1 * 1 / (ms_c[0] * 1e3), w1 * 2 / (ms_c[1] * 1e3), w1 * 4 / (ms_c[2] * 1e3), w1 * 8 / (ms_c[3] * 1e3));
   printf("{\"sms\": %d, \"dmma_m8n8k4_tflops\": %.3f, \"dfma_tflops\": %.3f, \"dmma_per_sm_per_us\": %.2f}\n", sms,
          dmma_flops / (ms_dmma * 1e-3) / 1e12, dfma_flops / (ms_dfma * 1e-3) / 1e12,
          warps * iters * 8.0 / sms / (ms_dmma * 1e3));
