@@ -162,6 +162,11 @@ int ensure_dense(dpgo_problem *p) {
       segptr[(size_t)J + 1] = segptr[(size_t)J] + (s1 + 7) / 8;
     }
     const int nchunks = segptr[(size_t)nseg];
+    // cost model of one chunk in column units: streamed width + a fixed part.  Measured on sphere2500 (phase clock,
+    // dense apply): fixed = 48 -> 99.5 us, 160 -> 93.1, 320 -> 88.2, 720 -> 83.9, 1000 -> 83.7: a chunk costs about the
+    // same whatever its width (waits, fragment parking, the masked diagonal path), so the runs are cut to nearly equal
+    // chunk COUNTS.  DPGO_SYM_CHUNK_COST overrides for tuning.
+    static const double chunk_cost = [] { const char *e4 = std::getenv("DPGO_SYM_CHUNK_COST"); return e4 ? std::atof(e4) : 800.0; }();
     std::vector<double> cum((size_t)nchunks + 1, 0.0);
     std::vector<long long> off((size_t)nchunks + 1, 0);      // chunk-major packed layout: 8 rows x (width up to 8, + 4) doubles
     {
@@ -170,7 +175,7 @@ int ensure_dense(dpgo_problem *p) {
         const int s0 = J * SEG, s1 = (int)std::min<int64_t>(N, (int64_t)s0 + SEG);
         for (int g = 0; 8 * g < s1; ++g, ++lin) {
           const int width = s1 - std::max(s0, 8 * g);
-          cum[(size_t)lin + 1] = cum[(size_t)lin] + (double)width + 48.0;
+          cum[(size_t)lin + 1] = cum[(size_t)lin] + (double)width + chunk_cost;
           off[(size_t)lin + 1] = off[(size_t)lin] + 8LL * (((width + 7) & ~7) + 4);
         }
       }

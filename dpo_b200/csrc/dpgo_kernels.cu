@@ -301,7 +301,7 @@ template <int R> __device__ void phase_dense(const KParams &kp, const double *V,
 constexpr int DENSE_NST = 6;
 constexpr int DENSE_CONS = OPT_THREADS - 32;          // 480 consumer threads
 constexpr int DENSE_SEG = DENSE_CONS * 4;             // 1920 columns per chunk
-constexpr int DENSE_RING_DOUBLES = 5 * (8 * ((OPT_THREADS / 32 - 1) * 32 + 4) + 8 * 5);   // max(6 x 1920, the symmetric variant's 5 stages) doubles
+constexpr int DENSE_RING_DOUBLES = 6 * (8 * ((OPT_THREADS / 32 - 1) * 32 + 4) + 8 * 5);   // max(6 x 1920, the symmetric variant's 6 stages) doubles
 static_assert(DENSE_RING_DOUBLES >= DENSE_NST * DENSE_SEG, "ring must hold the full-matrix stages too");
 
 struct DenseRing {
@@ -434,14 +434,14 @@ template <int R> __device__ void phase_dense_tma(const KParams &kp, const double
 // Warp 15 is the producer (bulk TMA: one copy per chunk + the 8 V columns of the group, L2 evict-first for the
 // matrix), warps 0..14 consume through full/empty mbarriers; the consumers park their transposed fragments in shared
 // memory and meet at a named barrier once per SYM_WIN/2 chunks; the sum over the warps overlaps the next chunks.
-constexpr int SYM_NST = 5;
+constexpr int SYM_NST = 6;
 constexpr int SYM_SEG = (OPT_THREADS / 32 - 1) * 32;   // 480 columns per segment: 32 per consumer warp
 constexpr int SYM_SROW = SYM_SEG + 4;                   // staged row pitch: 3872 B = 32 mod 128 (conflict-light tile reads)
 constexpr int SYM_VOFF = 8 * SYM_SROW;                  // the group's V columns (8 x R doubles) follow the 8 rows
 constexpr int SYM_STAGE = SYM_VOFF + 8 * 5;             // doubles per stage (R <= 5)
 constexpr int SYM_RING_DOUBLES = SYM_NST * SYM_STAGE;
 static_assert(SYM_RING_DOUBLES <= DENSE_RING_DOUBLES && SYM_NST <= DENSE_NST, "ring too small for the symmetric variant");
-constexpr int SYM_WIN = 8;                              // chunks per transposed-fragment window
+constexpr int SYM_WIN = 4;                              // chunks per transposed-fragment window
 constexpr int SYM_META_DOUBLES = SYM_WIN;               // 2 ints per window slot: segment, first row
 static_assert((OPT_THREADS / 32 - 1) * SYM_WIN * 8 * 5 <= DENSE_PER_MAX * 5, "the fragment window lives in the V staging area");
 
@@ -792,18 +792,14 @@ template <int R, int DH> __global__ void __launch_bounds__(OPT_THREADS, 1) k_opt
   bc.parity = 0;
   // diagnostic phase clock: CTA 0 / thread 0 charges the time since the previous tick to a phase kind
   // (0 eval, 1 dense apply, 2 partial sums + projection, 3 Hessian product, 4 tCG update, 5 retraction, 6 final)
-  // slot 7 accumulates SM cycles (clock64) over the same intervals: cycles / ns = the SM clock the kernel really ran at
   unsigned long long tick_last = 0;
-  long long tick_clk = 0;
   const bool ticking = (kp.phase_ns != nullptr) && blockIdx.x == 0 && threadIdx.x == 0;
   auto tick = [&](int kind) {
     if (ticking) {
       unsigned long long t;
       asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-      const long long ck = clock64();
-      if (kind >= 0) { kp.phase_ns[kind] += t - tick_last; kp.phase_ns[7] += (unsigned long long)(ck - tick_clk); }
+      if (kind >= 0) kp.phase_ns[kind] += t - tick_last;
       tick_last = t;
-      tick_clk = ck;
     }
   };
   tick(-1);

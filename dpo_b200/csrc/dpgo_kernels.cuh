@@ -33,7 +33,7 @@ enum OpCode {
 constexpr int NRED = 4;            // scalars reduced per phase
 constexpr int OPT_THREADS = 512;   // persistent kernel block size
 constexpr int SPMV_GROUP_BLOCKS = 192;  // blocks per row group of the TMA-fed SpMV (24 KB of Q per smem stage)
-constexpr int DENSE_PER_MAX = 1024; // max rows of the dense inverse one CTA owns (smem staging of V)
+constexpr int DENSE_PER_MAX = 512;  // max rows of the dense inverse one CTA owns (smem staging of V): N <= 75k at 148 CTAs
 
 struct KParams {
   int n;                 // poses

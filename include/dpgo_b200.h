@@ -191,8 +191,7 @@ DPGO_API int dpgo_debug_phase_latency(dpgo_problem_t *p, int phases, double *us_
 /* diagnostic: phase clock of the persistent kernel.  enable != 0 switches it on (subsequent optimise calls
  * accumulate, per phase kind, the nanoseconds CTA 0 spent up to the closing grid barrier); every call returns the
  * accumulated milliseconds in ms_by_kind[8] (0 eval pass, 1 dense preconditioner apply, 2 partial sums + projection,
- * 3 Hessian product, 4 tCG update, 5 retraction, 6 final; slot 7 = SM cycles (clock64) / 1e6 over the same intervals,
- * so cycles / ns gives the SM clock the kernel ran at) and resets them; enable == 0 switches it off. */
+ * 3 Hessian product, 4 tCG update, 5 retraction, 6 final, 7 unused) and resets them; enable == 0 switches it off. */
 DPGO_API int dpgo_debug_phase_times(dpgo_problem_t *p, int enable, double *ms_by_kind);
 
 /* ---- boundary-pose exchange (multi-agent, one agent per GPU) ----------------------------- */

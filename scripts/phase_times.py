@@ -64,8 +64,7 @@ def main():
            "ms_per_step_events": e0.elapsed_time(e1) / args.steps, "precond_applies": applies, "q_passes": passes,
            "ms_per_step_by_kind": {k: ms[i] / args.steps for i, k in enumerate(KINDS) if ms[i] > 0},
            "us_per_dense_apply": 1e3 * ms[1] / max(applies, 1), "us_per_partial_sum": 1e3 * ms[2] / max(applies, 1),
-           "us_per_hessian": 1e3 * ms[3] / max(passes - 2 * args.steps, 1),
-           "sm_mhz_in_kernel": 1e3 * ms[7] / max(sum(ms[i] for i in range(7)), 1e-9)}
+           "us_per_hessian": 1e3 * ms[3] / max(passes - 2 * args.steps, 1)}
     print(json.dumps(out))
 
 
