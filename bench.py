@@ -384,34 +384,25 @@ def run_gpu_arm(args):
         cols = (run.glob[rank][:, None] * dh + np.arange(dh)[None, :]).ravel()
         X0d = torch.from_numpy(np.asfortranarray(X0[:, cols]).ravel(order="F").copy()).to(dev)
         rounds_per_cycle = CYCLE * run.ncolours
-        steps_per_cycle = sum(1 for i in range(rounds_per_cycle) if run.colour[rank] == i % run.ncolours)
 
-        def one_cycle():
-            ag.mProblem.copy_X_from_device(X0d.data_ptr())
-            for i in range(rounds_per_cycle):
-                run.exchange()
-                if run.colour[rank] == i % run.ncolours:
-                    ag.opt.optimize_resident_async()
+        def run_rounds(count):
+            """`count` RBCD rounds; the iterate is reset to the initial point at the start of every cycle."""
+            mine = 0
+            with torch.cuda.stream(side):
+                for i in range(count):
+                    c = i % rounds_per_cycle
+                    if c == 0:
+                        ag.mProblem.copy_X_from_device(X0d.data_ptr())
+                    run.exchange()
+                    if run.colour[rank] == c % run.ncolours:
+                        ag.opt.optimize_resident_async()
+                        mine += 1
+            return mine
 
-        ncycles = max(1, K // rounds_per_cycle)
-        K = ncycles * rounds_per_cycle             # timed rounds: whole cycles
         # (capturing a cycle -- cooperative kernels + NCCL all-gathers -- into one CUDA graph was tried and hangs at
         #  replay on this stack, so the rounds are launched eagerly from the host)
-        graph, graph_note = None, "eager launches"
-        with torch.cuda.stream(side):
-            for _ in range(max(2, (W + rounds_per_cycle - 1) // rounds_per_cycle)):
-                one_cycle()
-        barrier()
-
-        def run_cycles(count):
-            with torch.cuda.stream(side):
-                for _ in range(count):
-                    if graph is not None:
-                        graph.replay()
-                    else:
-                        one_cycle()
-
-        run_cycles(2)
+        graph_note = "eager launches"
+        run_rounds(max(W, 2 * rounds_per_cycle))
         barrier()
         sampler = ClockSampler(local_rank)
         if rank == 0:
@@ -420,11 +411,10 @@ def run_gpu_arm(args):
         barrier()
         with torch.cuda.stream(side):
             e0.record()
-        run_cycles(ncycles)
+        my_steps = run_rounds(K)                     # exactly K timed rounds
         with torch.cuda.stream(side):
             e1.record()
         barrier()
-        my_steps = ncycles * steps_per_cycle
         t = torch.tensor([e0.elapsed_time(e1), float(my_steps)], dtype=torch.float64, device=dev)
         tmax = t.clone()
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
