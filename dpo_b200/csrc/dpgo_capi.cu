@@ -111,8 +111,6 @@ void fill_kparams(const dpgo_problem *p, dpgo::KParams &kp, int op, const dpgo_o
   kp.bar_counter = p->d_bar;
   kp.bar_epoch = p->d_bar + 1;
   kp.phase_ns = p->d_phase_ns;
-  static const int dbg_mask = [] { const char *e3 = std::getenv("DPGO_SYM_DEBUG"); return e3 ? std::atoi(e3) : 0; }();
-  kp.dbg = dbg_mask;   // experiments only (skips work: wrong results)
   kp.prm = prm;
   kp.result = p->d_result;
 }

@@ -424,8 +424,8 @@ template <int R> __device__ void phase_dense_tma(const KParams &kp, const double
 //   transposed  T[:, g0..]    += V[:, ctile..] * P[g0.., ctile..]^T    (per chunk; summed over the 15 consumer warps)
 // and the diagonal tile feeds the direct product only.  Both are mma.sync m8n8k4 (DMMA): the 8x8 tile is read from
 // shared memory in the two B-fragment layouts, so the k-reduction of the transposed product happens inside the tensor
-// op.  The chunks are ordered segment-major and the host cuts that sequence into `grid` contiguous runs of equal
-// streamed bytes (+ a fixed cost per chunk), so a CTA works inside one or two segments:
+// op.  The chunks are ordered segment-major and the host cuts that sequence into `grid` contiguous runs of equal cost
+// (a chunk costs about the same whatever its width, see ensure_dense), so a CTA works inside one or two segments:
 //   * direct partials: one panel slot per (CTA, segment) -- ~grid/nseg+1 slots per column instead of `grid`;
 //   * transposed results: chunk (J, g) is owned by exactly one CTA, which writes rows 8g..8g+7 of slot J of dense_t2.
 // phase_pz adds, per element, the <= ccount[J] panel slots and the <= nseg transposed slots in fixed order.

@@ -64,7 +64,6 @@ struct KParams {
   unsigned *bar_epoch;
   dpgo_opt_params_t prm;
   dpgo_opt_result_t *result;   // device copy of the result record
-  int dbg;                     // experiment switches (DPGO_SYM_DEBUG bitmask; 0 in production)
   unsigned long long *phase_ns; // diagnostic (nullable): per phase kind, ns seen by CTA 0 (dpgo_debug_phase_times)
 };
 
