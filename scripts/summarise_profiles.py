@@ -82,8 +82,8 @@ def summarise_launches(csv_path, path):
         fh.write("# Launch list of `bench.py --steps 12 --warmup 3 --no-cpu` under ncu\n\n"
                  f"source: `{os.path.relpath(csv_path, ROOT)}` (`ncu --metrics gpu__time_duration.sum --clock-control none`; "
                  "per-launch times are cold-cache and serialised: compare SHARES, not absolutes).\n\n"
-                 "The `k_gj_*` / `k_bsr_to_dense` launches are the one-shot setup of the dense preconditioner (setQ), not the "
-                 "timed step; the timed step is exactly one `k_optimize` launch.\n\n"
+                 "The `k_gj_*` / `k_bsr_to_dense` / `k_pack_sym` launches are the one-shot setup of the dense preconditioner "
+                 "(first exact-mode use), not the timed step; the timed step is exactly one `k_optimize` launch.\n\n"
                  "| kernel | launches | total us | share | grid | block |\n|---|---|---|---|---|---|\n")
         for name, (cnt, t, g, b) in sorted(per.items(), key=lambda kv: -kv[1][1]):
             fh.write(f"| {name} | {cnt} | {t / 1e3:.1f} | {100 * t / total:.1f}% | {g} | {b} |\n")
