@@ -10,9 +10,9 @@
 namespace DPGO {
 
 QuadraticOptimizer::QuadraticOptimizer(QuadraticProblem *p)
-    : problem(p), algorithm(ROPTALG::RTR), gradientDescentStepsize(1e-3), trustRegionIterations(1),
-      trustRegionTolerance(1e-2), trustRegionInitialRadius(1e1), trustRegionMaxInnerIterations(50),
-      preconditioner(Preconditioner::DenseExact), verbose(false) {
+    : problem(p), algorithm(ROPTALG::RTR), preconditioner(Preconditioner::DenseExact), gradientDescentStepsize(1e-3),
+      trustRegionTolerance(1e-2), trustRegionInitialRadius(1e1), trustRegionIterations(1),
+      trustRegionMaxInnerIterations(50), verbose(false) {
   result.success = false;
 }
 
