@@ -84,6 +84,8 @@ SIGNATURES = {
     "dpgo_spmv_device": (C.c_int, [_vp, _vp, _vp, C.c_int]),
     "dpgo_spmv_algorithmic_bytes": (C.c_int64, [_vp, C.c_int]),
     "dpgo_precond_algorithmic_bytes": (C.c_int64, [_vp, C.c_int]),
+    "dpgo_sym_plan_sizes": (C.c_int, [C.c_int, _ip, _ip]),
+    "dpgo_sym_plan": (C.c_int, [C.c_int, C.c_int, C.c_double, _ip, _ip, _ip, _ip, C.POINTER(C.c_int64)]),
     "dpgo_debug_phase_latency": (C.c_int, [_vp, C.c_int, _dp, _dp]),
     "dpgo_debug_phase_times": (C.c_int, [_vp, C.c_int, _dp]),
     "dpgo_agent_set_public_poses": (C.c_int, [_vp, C.c_int, _ip]),

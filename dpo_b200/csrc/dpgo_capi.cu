@@ -123,6 +123,75 @@ cudaError_t run_spmv(const dpgo_problem *p, const double *X, const double *G, do
   return dpgo::launch_spmv(p->r, p->dh, p->n, p->d_rowptr, p->d_bcol, p->d_bval, X, G, out, p->stream);
 }
 
+// Work decomposition of the symmetric (upper-triangle) dense apply (phase_dense_sym) -- host only, also exported as
+// dpgo_sym_plan so that CPU tests can check it.  Chunks (segment J of 480 columns, 8-row group g with 8g < end of J) in
+// segment-major order are cut into `grid` contiguous runs of equal cost; per segment the consecutive CTAs that touch it
+// get the partial-panel slots 0..ccount-1; `off` is the chunk-major packed layout (8 rows x (width up to 8, + 4) doubles).
+// Cost model of one chunk in column units: streamed width + a fixed part.  Measured on sphere2500 (phase clock, dense
+// apply): fixed = 48 -> 99.5 us, 160 -> 93.1, 320 -> 88.2, 720 -> 83.9, 1000 -> 83.7: a chunk costs about the same
+// whatever its width (waits, fragment parking, the masked diagonal path), so the runs get nearly equal chunk COUNTS.
+constexpr double SYM_CHUNK_COST = 800.0;
+constexpr int SYM_PLAN_SEG = 480;      // = dpgo::SYM_SEG of the kernel (15 consumer warps x 32 columns)
+
+struct SymPlan {
+  int nseg = 0, nchunks = 0;
+  std::vector<int> segptr, cut, cfirst, ccount;
+  std::vector<long long> off;
+};
+
+bool make_sym_plan(int64_t N, int G, double chunk_cost, SymPlan &pl) {
+  if (N % 2 != 0 || N < 2048 || G < 1) return false;       // bulk TMA needs 16-byte aligned rows; small N: plain apply
+  const int SEG = SYM_PLAN_SEG, nseg = (int)((N + SEG - 1) / SEG);
+  pl.nseg = nseg;
+  pl.segptr.assign((size_t)nseg + 1, 0);
+  for (int J = 0; J < nseg; ++J) {
+    const int s1 = (int)std::min<int64_t>(N, (int64_t)(J + 1) * SEG);
+    pl.segptr[(size_t)J + 1] = pl.segptr[(size_t)J] + (s1 + 7) / 8;
+  }
+  const int nchunks = pl.nchunks = pl.segptr[(size_t)nseg];
+  std::vector<double> cum((size_t)nchunks + 1, 0.0);
+  pl.off.assign((size_t)nchunks + 1, 0);
+  {
+    int lin = 0;
+    for (int J = 0; J < nseg; ++J) {
+      const int s0 = J * SEG, s1 = (int)std::min<int64_t>(N, (int64_t)s0 + SEG);
+      for (int g = 0; 8 * g < s1; ++g, ++lin) {
+        const int width = s1 - std::max(s0, 8 * g);
+        cum[(size_t)lin + 1] = cum[(size_t)lin] + (double)width + chunk_cost;
+        pl.off[(size_t)lin + 1] = pl.off[(size_t)lin] + 8LL * (((width + 7) & ~7) + 4);
+      }
+    }
+  }
+  pl.cut.assign((size_t)G + 1, 0);
+  {
+    int lin = 0;
+    for (int b = 1; b < G; ++b) {
+      const double target = cum[(size_t)nchunks] * b / G;
+      while (lin < nchunks && cum[(size_t)lin + 1] <= target) ++lin;
+      pl.cut[(size_t)b] = lin;
+    }
+    pl.cut[(size_t)G] = nchunks;
+  }
+  pl.cfirst.assign((size_t)nseg, 0);
+  pl.ccount.assign((size_t)nseg, 0);
+  int maxslots = 0;
+  for (int J = 0; J < nseg; ++J) {
+    int first = -1, last = -1;
+    for (int b = 0; b < G; ++b)
+      if (pl.cut[(size_t)b] < pl.segptr[(size_t)J + 1] && pl.cut[(size_t)b + 1] > pl.segptr[(size_t)J] &&
+          pl.cut[(size_t)b] < pl.cut[(size_t)b + 1]) {
+        if (first < 0) first = b;
+        last = b;
+      }
+    pl.cfirst[(size_t)J] = std::max(first, 0);
+    pl.ccount[(size_t)J] = (first < 0) ? 0 : last - first + 1;
+    maxslots = std::max(maxslots, pl.ccount[(size_t)J]);
+  }
+  bool runs_ok = (maxslots <= G);   // the panels live in dense_part (grid x r x N)
+  for (int b = 0; b < G; ++b) runs_ok = runs_ok && (pl.cut[(size_t)b] < pl.cut[(size_t)b + 1]);   // slots assume no empty run
+  return runs_ok;
+}
+
 // The dense inverse (Q + 0.1 I)^-1 is built on first use (one-shot: scatter block-CSR into N x N in HBM, blocked
 // Gauss-Jordan in place) -- problems that are only evaluated (e.g. the drivers' centralised problem) never pay for it.
 int ensure_dense(dpgo_problem *p) {
@@ -147,80 +216,29 @@ int ensure_dense(dpgo_problem *p) {
     free_dev(p->d_dense_part);
     return fail(DPGO_ERR_CUDA, std::string("dense preconditioner setup: ") + cudaGetErrorString(e));
   }
-  // Plan of the symmetric (upper-triangle) variant (phase_dense_sym): chunks (segment J of 480 columns, 8-row group g
-  // with 8g < end of J) in segment-major order, cut into `grid` contiguous runs of equal cost (streamed columns + a
-  // fixed per-chunk cost); per segment the consecutive CTAs that touch it get the partial-panel slots 0..ccount-1.
+  // symmetric (upper-triangle) variant: plan, packed copy, partial buffers (falls back to the full matrix otherwise)
   static const bool no_sym = [] { const char *e2 = std::getenv("DPGO_DENSE_FULL"); return e2 && e2[0] == '1'; }();
+  static const double chunk_cost = [] { const char *e4 = std::getenv("DPGO_SYM_CHUNK_COST"); return e4 ? std::atof(e4) : SYM_CHUNK_COST; }();
   p->sym_ok = 0;
-  if (!no_sym && (N % 2 == 0) && N >= 2048) {
-    const int G = p->grid, SEG = 480, nseg = (int)((N + SEG - 1) / SEG);
-    std::vector<int> segptr((size_t)nseg + 1, 0);
-    for (int J = 0; J < nseg; ++J) {
-      const int s1 = (int)std::min<int64_t>(N, (int64_t)(J + 1) * SEG);
-      segptr[(size_t)J + 1] = segptr[(size_t)J] + (s1 + 7) / 8;
-    }
-    const int nchunks = segptr[(size_t)nseg];
-    // cost model of one chunk in column units: streamed width + a fixed part.  Measured on sphere2500 (phase clock,
-    // dense apply): fixed = 48 -> 99.5 us, 160 -> 93.1, 320 -> 88.2, 720 -> 83.9, 1000 -> 83.7: a chunk costs about the
-    // same whatever its width (waits, fragment parking, the masked diagonal path), so the runs are cut to nearly equal
-    // chunk COUNTS.  DPGO_SYM_CHUNK_COST overrides for tuning.
-    static const double chunk_cost = [] { const char *e4 = std::getenv("DPGO_SYM_CHUNK_COST"); return e4 ? std::atof(e4) : 800.0; }();
-    std::vector<double> cum((size_t)nchunks + 1, 0.0);
-    std::vector<long long> off((size_t)nchunks + 1, 0);      // chunk-major packed layout: 8 rows x (width up to 8, + 4) doubles
-    {
-      int lin = 0;
-      for (int J = 0; J < nseg; ++J) {
-        const int s0 = J * SEG, s1 = (int)std::min<int64_t>(N, (int64_t)s0 + SEG);
-        for (int g = 0; 8 * g < s1; ++g, ++lin) {
-          const int width = s1 - std::max(s0, 8 * g);
-          cum[(size_t)lin + 1] = cum[(size_t)lin] + (double)width + chunk_cost;
-          off[(size_t)lin + 1] = off[(size_t)lin] + 8LL * (((width + 7) & ~7) + 4);
-        }
-      }
-    }
-    std::vector<int> cut((size_t)G + 1, 0);
-    {
-      int lin = 0;
-      for (int b = 1; b < G; ++b) {
-        const double target = cum[(size_t)nchunks] * b / G;
-        while (lin < nchunks && cum[(size_t)lin + 1] <= target) ++lin;
-        cut[(size_t)b] = lin;
-      }
-      cut[(size_t)G] = nchunks;
-    }
-    std::vector<int> cfirst((size_t)nseg, 0), ccount((size_t)nseg, 0);
-    int maxslots = 0;
-    for (int J = 0; J < nseg; ++J) {
-      int first = -1, last = -1;
-      for (int b = 0; b < G; ++b)
-        if (cut[(size_t)b] < segptr[(size_t)J + 1] && cut[(size_t)b + 1] > segptr[(size_t)J] && cut[(size_t)b] < cut[(size_t)b + 1]) {
-          if (first < 0) first = b;
-          last = b;
-        }
-      cfirst[(size_t)J] = std::max(first, 0);
-      ccount[(size_t)J] = (first < 0) ? 0 : last - first + 1;
-      maxslots = std::max(maxslots, ccount[(size_t)J]);
-    }
-    bool runs_ok = (maxslots <= G);   // the panels live in dense_part (grid x r x N)
-    for (int b = 0; b < G; ++b) runs_ok = runs_ok && (cut[(size_t)b] < cut[(size_t)b + 1]);   // slots assume no empty run
-    if (runs_ok) {
-      DPGO_CUDA(cudaMalloc(&p->d_sym_cut, sizeof(int) * cut.size()));
-      DPGO_CUDA(cudaMalloc(&p->d_sym_segptr, sizeof(int) * segptr.size()));
-      DPGO_CUDA(cudaMalloc(&p->d_sym_cfirst, sizeof(int) * cfirst.size()));
-      DPGO_CUDA(cudaMalloc(&p->d_sym_ccount, sizeof(int) * ccount.size()));
-      DPGO_CUDA(cudaMalloc(&p->d_dense_t2, sizeof(double) * (size_t)nseg * p->r * N));
-      DPGO_CUDA(cudaMemset(p->d_dense_t2, 0, sizeof(double) * (size_t)nseg * p->r * N));
-      DPGO_CUDA(cudaMalloc(&p->d_sym_off, sizeof(long long) * off.size()));
-      DPGO_CUDA(cudaMalloc(&p->d_ppack, sizeof(double) * (size_t)off[(size_t)nchunks]));
-      DPGO_CUDA(cudaMemcpy(p->d_sym_off, off.data(), sizeof(long long) * off.size(), cudaMemcpyHostToDevice));
-      DPGO_CUDA(cudaMemcpy(p->d_sym_cut, cut.data(), sizeof(int) * cut.size(), cudaMemcpyHostToDevice));
-      DPGO_CUDA(cudaMemcpy(p->d_sym_segptr, segptr.data(), sizeof(int) * segptr.size(), cudaMemcpyHostToDevice));
-      DPGO_CUDA(cudaMemcpy(p->d_sym_cfirst, cfirst.data(), sizeof(int) * cfirst.size(), cudaMemcpyHostToDevice));
-      DPGO_CUDA(cudaMemcpy(p->d_sym_ccount, ccount.data(), sizeof(int) * ccount.size(), cudaMemcpyHostToDevice));
-      DPGO_CUDA(dpgo::launch_pack_sym(p->d_pinv, (int)N, nchunks, p->d_sym_segptr, nseg, p->d_sym_off, p->d_ppack, p->stream));
-      DPGO_CUDA(cudaStreamSynchronize(p->stream));
-      p->sym_ok = 1;
-    }
+  SymPlan plan;
+  if (!no_sym && make_sym_plan((int64_t)N, p->grid, chunk_cost, plan)) {
+    const int nseg = plan.nseg, nchunks = plan.nchunks;
+    DPGO_CUDA(cudaMalloc(&p->d_sym_cut, sizeof(int) * plan.cut.size()));
+    DPGO_CUDA(cudaMalloc(&p->d_sym_segptr, sizeof(int) * plan.segptr.size()));
+    DPGO_CUDA(cudaMalloc(&p->d_sym_cfirst, sizeof(int) * plan.cfirst.size()));
+    DPGO_CUDA(cudaMalloc(&p->d_sym_ccount, sizeof(int) * plan.ccount.size()));
+    DPGO_CUDA(cudaMalloc(&p->d_dense_t2, sizeof(double) * (size_t)nseg * p->r * N));
+    DPGO_CUDA(cudaMemset(p->d_dense_t2, 0, sizeof(double) * (size_t)nseg * p->r * N));
+    DPGO_CUDA(cudaMalloc(&p->d_sym_off, sizeof(long long) * plan.off.size()));
+    DPGO_CUDA(cudaMalloc(&p->d_ppack, sizeof(double) * (size_t)plan.off[(size_t)nchunks]));
+    DPGO_CUDA(cudaMemcpy(p->d_sym_off, plan.off.data(), sizeof(long long) * plan.off.size(), cudaMemcpyHostToDevice));
+    DPGO_CUDA(cudaMemcpy(p->d_sym_cut, plan.cut.data(), sizeof(int) * plan.cut.size(), cudaMemcpyHostToDevice));
+    DPGO_CUDA(cudaMemcpy(p->d_sym_segptr, plan.segptr.data(), sizeof(int) * plan.segptr.size(), cudaMemcpyHostToDevice));
+    DPGO_CUDA(cudaMemcpy(p->d_sym_cfirst, plan.cfirst.data(), sizeof(int) * plan.cfirst.size(), cudaMemcpyHostToDevice));
+    DPGO_CUDA(cudaMemcpy(p->d_sym_ccount, plan.ccount.data(), sizeof(int) * plan.ccount.size(), cudaMemcpyHostToDevice));
+    DPGO_CUDA(dpgo::launch_pack_sym(p->d_pinv, (int)N, nchunks, p->d_sym_segptr, nseg, p->d_sym_off, p->d_ppack, p->stream));
+    DPGO_CUDA(cudaStreamSynchronize(p->stream));
+    p->sym_ok = 1;
   }
   return DPGO_OK;
 }
@@ -863,6 +881,31 @@ int64_t dpgo_spmv_algorithmic_bytes(const dpgo_problem_t *p, int add_G) {
   int64_t b = p->nb * (dh * dh * 8 + 4) + ((int64_t)p->n + 1) * 4 + 2 * (int64_t)p->r * dh * p->n * 8;
   if (add_G) b += (int64_t)p->r * dh * p->n * 8;
   return b;
+}
+
+int dpgo_sym_plan_sizes(int N, int *num_segments, int *num_chunks) {
+  DPGO_REQUIRE(num_segments && num_chunks, DPGO_ERR_INVALID_ARG, "null argument");
+  DPGO_REQUIRE(N >= 1, DPGO_ERR_INVALID_ARG, "bad dimension");
+  const int nseg = (N + SYM_PLAN_SEG - 1) / SYM_PLAN_SEG;
+  int nch = 0;
+  for (int J = 0; J < nseg; ++J) nch += (std::min(N, (J + 1) * SYM_PLAN_SEG) + 7) / 8;
+  *num_segments = nseg;
+  *num_chunks = nch;
+  return DPGO_OK;
+}
+
+int dpgo_sym_plan(int N, int grid, double chunk_cost, int32_t *segptr, int32_t *cut, int32_t *cfirst, int32_t *ccount,
+                  int64_t *chunk_offset) {
+  DPGO_REQUIRE(segptr && cut && cfirst && ccount && chunk_offset, DPGO_ERR_INVALID_ARG, "null argument");
+  SymPlan pl;
+  if (!make_sym_plan((int64_t)N, grid, chunk_cost > 0 ? chunk_cost : SYM_CHUNK_COST, pl))
+    return fail(DPGO_ERR_UNSUPPORTED, "no symmetric plan for this size (odd N, N < 2048, or more CTAs than chunks)");
+  std::copy(pl.segptr.begin(), pl.segptr.end(), segptr);
+  std::copy(pl.cut.begin(), pl.cut.end(), cut);
+  std::copy(pl.cfirst.begin(), pl.cfirst.end(), cfirst);
+  std::copy(pl.ccount.begin(), pl.ccount.end(), ccount);
+  std::copy(pl.off.begin(), pl.off.end(), chunk_offset);
+  return DPGO_OK;
 }
 
 int64_t dpgo_precond_algorithmic_bytes(const dpgo_problem_t *p, int preconditioner) {

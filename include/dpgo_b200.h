@@ -186,6 +186,15 @@ DPGO_API int64_t dpgo_spmv_algorithmic_bytes(const dpgo_problem_t *p, int add_G)
  * has to move: the operator's unique data (upper triangle of the symmetric dense inverse when the symmetric
  * kernel is planned, i.e. after the first exact-mode optimise; the full matrix otherwise) + input and output vector */
 DPGO_API int64_t dpgo_precond_algorithmic_bytes(const dpgo_problem_t *p, int preconditioner);
+/* host only (no device needed): the work decomposition the symmetric dense apply uses for an N x N operator on `grid`
+ * CTAs -- column segments of 480, 8-row groups, chunks in segment-major order.  segptr[nseg+1] = first chunk of every
+ * segment, cut[grid+1] = chunk range of every CTA, cfirst/ccount[nseg] = the consecutive CTAs that touch a segment
+ * (= partial-panel slots of its columns), chunk_offset[nchunks+1] = first double of every chunk in the packed upper
+ * triangle.  chunk_cost <= 0 selects the built-in cost model.  DPGO_ERR_UNSUPPORTED when no plan exists for this size
+ * (odd N, N < 2048, fewer chunks than CTAs); the library then streams the full matrix. */
+DPGO_API int dpgo_sym_plan_sizes(int N, int *num_segments, int *num_chunks);
+DPGO_API int dpgo_sym_plan(int N, int grid, double chunk_cost, int32_t *segptr, int32_t *cut, int32_t *cfirst,
+                           int32_t *ccount, int64_t *chunk_offset);
 /* diagnostic: cost of one empty phase of the persistent kernel (grid barrier + scalar reduction) and of its launch */
 DPGO_API int dpgo_debug_phase_latency(dpgo_problem_t *p, int phases, double *us_per_phase, double *us_launch);
 /* diagnostic: phase clock of the persistent kernel.  enable != 0 switches it on (subsequent optimise calls
