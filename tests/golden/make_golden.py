@@ -1,0 +1,42 @@
+#!/usr/bin/env python
+"""Regenerates tests/golden/NP<dataset>_head400.txt: the first 400 lines of the convergence traces the reference
+ships under result/graph/ (one line per RBCD iteration of its 5-robot MultiRobotExample run: `2 f, |grad|`, written by
+examples/MultiRobotExample.cpp:291-300, file opened at :224).  They are copied verbatim -- the reference's own outputs are the golden
+vectors; nothing here is computed by this repository.
+
+Run in a container that has the reference mounted (it does not exist on the GPU box):
+    python tests/golden/make_golden.py [--reference /root/reference] [--check]
+"""
+import argparse
+import os
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+DATASETS = ["CSAIL", "grid3D", "parking-garage", "smallGrid3D", "sphere2500", "torus3D"]
+LINES = 400
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--reference", default="/root/reference")
+    ap.add_argument("--check", action="store_true", help="compare the committed fixtures instead of rewriting them")
+    args = ap.parse_args()
+    bad = 0
+    for ds in DATASETS:
+        src = os.path.join(args.reference, "result", "graph", f"NP{ds}.txt")
+        dst = os.path.join(HERE, f"NP{ds}_head400.txt")
+        with open(src) as fh:
+            head = "".join(fh.readlines()[:LINES])
+        if args.check:
+            same = os.path.exists(dst) and open(dst).read() == head
+            print(f"{ds}: {'identical' if same else 'DIFFERS'}")
+            bad += 0 if same else 1
+        else:
+            with open(dst, "w") as fh:
+                fh.write(head)
+            print(f"wrote {dst}")
+    sys.exit(1 if bad else 0)
+
+
+if __name__ == "__main__":
+    main()
