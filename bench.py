@@ -257,7 +257,8 @@ def run_gpu_arm(args):
         torch.cuda.synchronize()
 
     if world == 1:
-        prob = dp.QuadraticProblem(n, d, RANK_R, device=local_rank)
+        prob = dp.QuadraticProblem(n, d, RANK_R, device=local_rank,
+                                   preconditioners=(dp.PRECOND_BLOCK_JACOBI, dp.PRECOND_SPARSE_EXACT, dp.PRECOND_DENSE_EXACT))
         prob.setQ_blocks(*pg.connection_laplacian_blocks(edges))
         prob.set_stream(torch.cuda.current_stream().cuda_stream)
         opt = dp.QuadraticOptimizer(prob)
@@ -265,7 +266,8 @@ def run_gpu_arm(args):
         opt.setTrustRegionIterations(1)
         opt.setTrustRegionMaxInnerIterations(10)
         opt.setTrustRegionInitialRadius(100)
-        opt.setPreconditioner(dp.PRECOND_DENSE_EXACT)
+        PRE = dp.PRECOND_DENSE_EXACT if args.precond == "dense" else dp.PRECOND_SPARSE_EXACT
+        opt.setPreconditioner(PRE)
         X0d = torch.from_numpy(np.asfortranarray(X0).ravel(order="F").copy()).to(dev)
 
         def resident_steps(count, collect=None):
@@ -314,7 +316,7 @@ def run_gpu_arm(args):
         # ---- roofline of the dominant kernel of the step: the persistent k_optimize launch ----
         spmv_b = prob.spmv_algorithmic_bytes(True)
         N = (d + 1) * n
-        pre_b = prob.precond_algorithmic_bytes(dp.PRECOND_DENSE_EXACT)      # unique bytes (upper triangle if planned)
+        pre_b = prob.precond_algorithmic_bytes(PRE)      # bytes of the operator's blocks one application streams
         pre_full = N * N * 8 + 2 * vec_bytes                                # the full dense operator
         per_step, per_step_full, flops = [], [], []
         for rs in trail:
@@ -480,6 +482,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-spmv", action="store_true", help="skip the synthetic SpMV roofline leg")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--precond", default="sparse", choices=["sparse", "dense"],
+                    help="exact preconditioner implementation: nested-dissection block solve (default) or the dense inverse (A/B)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference_arm(args)

@@ -15,7 +15,7 @@ LIB_PATH = os.path.join(_HERE, "lib", "libdpgo_b200.so")
 
 OK = 0
 ALG_RTR, ALG_RGD = 0, 1
-PRECOND_NONE, PRECOND_BLOCK_JACOBI, PRECOND_DENSE_EXACT = 0, 1, 2
+PRECOND_NONE, PRECOND_BLOCK_JACOBI, PRECOND_DENSE_EXACT, PRECOND_SPARSE_EXACT = 0, 1, 2, 3
 TCG_NAMES = {0: "NEGCURVTURE", 1: "EXCREGION", 2: "LCON", 3: "SCON", 4: "MAXITER", -1: "NOT_RUN"}
 
 
@@ -86,6 +86,9 @@ SIGNATURES = {
     "dpgo_precond_algorithmic_bytes": (C.c_int64, [_vp, C.c_int]),
     "dpgo_sym_plan_sizes": (C.c_int, [C.c_int, _ip, _ip]),
     "dpgo_sym_plan": (C.c_int, [C.c_int, C.c_int, C.c_double, _ip, _ip, _ip, _ip, C.POINTER(C.c_int64)]),
+    "dpgo_nd_info": (C.c_int, [_vp, C.POINTER(C.c_int64)]),
+    "dpgo_nd_debug_emulate": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int64, _ip, _ip, _dp, C.c_double, C.c_int, C.c_int,
+                                        C.c_int, _dp, _dp, C.POINTER(C.c_int64)]),
     "dpgo_debug_phase_latency": (C.c_int, [_vp, C.c_int, _dp, _dp]),
     "dpgo_debug_phase_times": (C.c_int, [_vp, C.c_int, _dp]),
     "dpgo_agent_set_public_poses": (C.c_int, [_vp, C.c_int, _ip]),

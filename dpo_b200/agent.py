@@ -38,7 +38,7 @@ class PGOAgentParameters:
     maxNumIters: int = 500
     relChangeTol: float = 5e-3
     verbose: bool = False
-    preconditioner: int = capi.PRECOND_DENSE_EXACT      # B200 extension (reference operator by default)
+    preconditioner: int = capi.PRECOND_SPARSE_EXACT     # B200 extension (reference operator by default)
     device: int = 0
 
 
@@ -384,7 +384,7 @@ class DistributedPGO:
     """
 
     def __init__(self, edges: EdgeSet, n: int, k: int, r: int = 5, algorithm: int = ROPTALG.RTR,
-                 preconditioner: int = capi.PRECOND_DENSE_EXACT, schedule: str = "greedy",
+                 preconditioner: int = capi.PRECOND_SPARSE_EXACT, schedule: str = "greedy",
                  owner: Optional[np.ndarray] = None, X_init: Optional[np.ndarray] = None,
                  rank: Optional[int] = None, world: Optional[int] = None, device: int = 0, dist=None):
         import torch

@@ -15,7 +15,9 @@ CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIBDIR, "libdpgo_b200.so")
 SOURCES = ["dpgo_kernels.cu", "dpgo_spmv_tma.cu", "dense_inverse.cu", "dpgo_capi.cu"]
-HEADERS = ["dpgo_device.cuh", "dpgo_kernels.cuh", os.path.join("..", "..", "include", "dpgo_b200.h")]
+HOST_ONLY_SOURCES = ["nd_precond.cpp"]          # host planning code inside libdpgo_b200.so (g++, OpenMP)
+HEADERS = ["dpgo_device.cuh", "dpgo_kernels.cuh", "nd_precond.h", os.path.join("..", "..", "include", "dpgo_b200.h")]
+HOST_ONLY_FLAGS = ["-O3", "-std=c++17", "-fPIC", "-fvisibility=hidden", "-fopenmp", "-mavx2", "-mfma", "-Wall"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
          "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "-Xptxas", "-v"]
@@ -26,7 +28,7 @@ def _mtime(path: str) -> float:
 
 
 def needs_build() -> bool:
-    newest = max(_mtime(os.path.join(CSRC, f)) for f in SOURCES + HEADERS)
+    newest = max(_mtime(os.path.join(CSRC, f)) for f in SOURCES + HOST_ONLY_SOURCES + HEADERS)
     return _mtime(LIB) < newest
 
 
@@ -39,10 +41,13 @@ def build_library(force: bool = False, verbose: bool = False) -> str:
     hdr_time = max(_mtime(os.path.join(CSRC, h)) for h in HEADERS)
 
     def compile_one(src: str) -> str:
-        obj = os.path.join(objdir, src.replace(".cu", ".o"))
+        obj = os.path.join(objdir, src.replace(".cu", ".o").replace(".cpp", ".o"))
         if not force and _mtime(obj) >= max(_mtime(os.path.join(CSRC, src)), hdr_time):
             return obj
-        cmd = [NVCC] + FLAGS + ["-c", os.path.join(CSRC, src), "-o", obj]
+        if src.endswith(".cpp"):
+            cmd = [os.environ.get("CXX", "g++")] + HOST_ONLY_FLAGS + ["-c", os.path.join(CSRC, src), "-o", obj]
+        else:
+            cmd = [NVCC] + FLAGS + ["-c", os.path.join(CSRC, src), "-o", obj]
         res = subprocess.run(cmd, capture_output=True, text=True)
         log = os.path.join(objdir, src + ".ptxas.log")
         with open(log, "w") as fh:
@@ -53,9 +58,10 @@ def build_library(force: bool = False, verbose: bool = False) -> str:
             print(res.stderr, file=sys.stderr)
         return obj
 
-    with ThreadPoolExecutor(max_workers=len(SOURCES)) as ex:
-        objs = list(ex.map(compile_one, SOURCES))
-    cmd = [NVCC, "-shared", "-o", LIB] + objs + ["-gencode", "arch=compute_100a,code=sm_100a", "-cudart", "static"]
+    with ThreadPoolExecutor(max_workers=len(SOURCES) + len(HOST_ONLY_SOURCES)) as ex:
+        objs = list(ex.map(compile_one, SOURCES + HOST_ONLY_SOURCES))
+    cmd = [NVCC, "-shared", "-o", LIB] + objs + ["-gencode", "arch=compute_100a,code=sm_100a", "-cudart", "static",
+                                                  "-Xcompiler", "-fopenmp"]
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:
         raise RuntimeError(f"link failed:\n{res.stdout}\n{res.stderr}")

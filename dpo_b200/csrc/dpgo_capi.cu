@@ -35,6 +35,12 @@ int fail(int code, const std::string &msg) {
     if (!(cond)) return fail(code, msg); \
   } while (0)
 
+#define DPGO_TRY(expr)            \
+  do {                            \
+    int _s = (expr);              \
+    if (_s != DPGO_OK) return _s; \
+  } while (0)
+
 template <class T> void free_dev(T *&p) {
   if (p) cudaFree(p);
   p = nullptr;
@@ -59,6 +65,13 @@ struct dpgo_problem {
   double *d_ppack = nullptr;
   long long *d_sym_off = nullptr;
   int *d_sym_cut = nullptr, *d_sym_segptr = nullptr, *d_sym_cfirst = nullptr, *d_sym_ccount = nullptr;
+  // host copy of the block-CSR (lazy preconditioner setup) and the sparse exact preconditioner
+  std::vector<int> h_rowptr, h_bcol;
+  std::vector<double> h_bval;
+  bool nd_ready = false;
+  dpgo::KNd nd = {};
+  dpgo::nd::Hierarchy *nd_H = nullptr;
+  int64_t nd_info[16] = {};
   // vectors
   double *d_G = nullptr;
   double *d_vec[dpgo::V_COUNT] = {};
@@ -110,6 +123,8 @@ void fill_kparams(const dpgo_problem *p, dpgo::KParams &kp, int op, const dpgo_o
   kp.partials = p->d_partials;
   kp.bar_counter = p->d_bar;
   kp.bar_epoch = p->d_bar + 1;
+  kp.nd = p->nd;
+  if (!p->nd_ready) kp.nd.nphases = 0;
   kp.phase_ns = p->d_phase_ns;
   kp.prm = prm;
   kp.result = p->d_result;
@@ -243,8 +258,97 @@ int ensure_dense(dpgo_problem *p) {
   return DPGO_OK;
 }
 
+void nd_fill_info(const dpgo::nd::Hierarchy &H, const dpgo::nd::Plan &P, int64_t *info) {
+  for (int i = 0; i < 16; ++i) info[i] = 0;
+  int smax = 0, bmax = 0;
+  for (const auto &m : H.nodes) { smax = std::max(smax, (int)m.own.size() * H.dh); bmax = std::max(bmax, (int)m.bnd.size() * H.dh); }
+  info[0] = H.nstages; info[1] = (int64_t)H.nodes.size(); info[2] = (int64_t)P.phases.size(); info[3] = H.blob_doubles * 8;
+  info[4] = P.bytes_per_apply; info[5] = smax; info[6] = bmax; info[7] = H.nd_depth; info[8] = (int64_t)P.steps.size();
+  info[9] = (int64_t)P.jobs.size(); info[10] = (int64_t)P.epis.size(); info[11] = P.max_ytiles; info[12] = P.max_slots;
+}
+
+dpgo::nd::Options nd_options(int grid, int r) {
+  dpgo::nd::Options opt;
+  opt.grid = grid;
+  opt.r = r;
+  opt.warps = dpgo::OPT_THREADS / 32;
+  opt.ycap_tiles = dpgo::ND_YCAP_TILES;
+  opt.slot_cap = dpgo::ND_SLOT_CAP;
+  if (const char *e = std::getenv("DPGO_ND_CUTS")) opt.force_ncuts = std::atoi(e);
+  if (const char *e = std::getenv("DPGO_ND_LEAF")) opt.leaf_size = std::max(1, std::atoi(e));
+  if (const char *e = std::getenv("DPGO_ND_TPHASE_US")) opt.t_phase_us = std::atof(e);
+  if (const char *e = std::getenv("DPGO_ND_BW_GBS")) opt.bw_gbs = std::atof(e);
+  return opt;
+}
+
+template <class T> int upload_array(const std::vector<T> &h, const T *&d, cudaStream_t stream) {
+  T *ptr = nullptr;
+  const size_t bytes = sizeof(T) * std::max<size_t>(h.size(), 1);
+  DPGO_CUDA(cudaMalloc(&ptr, bytes));
+  if (!h.empty()) DPGO_CUDA(cudaMemcpyAsync(ptr, h.data(), sizeof(T) * h.size(), cudaMemcpyHostToDevice, stream));
+  d = ptr;
+  return DPGO_OK;
+}
+
+void free_nd(dpgo_problem *p) {
+  auto fr = [](const void *q) { if (q) cudaFree(const_cast<void *>(q)); };
+  fr(p->nd.phases); fr(p->nd.cta_step); fr(p->nd.steps); fr(p->nd.gathers); fr(p->nd.jobs); fr(p->nd.epis); fr(p->nd.csrc);
+  fr(p->nd.blob); fr(p->nd.TX); fr(p->nd.C);
+  p->nd = dpgo::KNd();
+  delete p->nd_H;
+  p->nd_H = nullptr;
+  p->nd_ready = false;
+}
+
+// The nested-dissection block factorisation of Q + 0.1 I is built on first use (host: ordering, symbolic, plan; the
+// dense algebra of large blocks on the device), like the dense inverse.
+int ensure_nd(dpgo_problem *p) {
+  if (p->nd_ready) return DPGO_OK;
+  if (!(p->precond_mask & (1u << DPGO_PRECOND_SPARSE_EXACT)))
+    return fail(DPGO_ERR_STATE, "sparse exact preconditioner was not requested in set_Q (precond_mask)");
+  namespace nd = dpgo::nd;
+  free_nd(p);
+  nd::Plan plan;
+  std::vector<double> blob;
+  nd::Hierarchy *H = new nd::Hierarchy();
+  try {
+    const nd::Options opt = nd_options(p->grid, p->r);
+    nd::BsrView Q{p->n, p->dh, p->h_rowptr.data(), p->h_bcol.data(), p->h_bval.data()};
+    nd::build_hierarchy(Q, opt, *H);
+    nd::build_numeric(Q, opt, *H, blob);
+    nd::build_plan(*H, opt, plan);
+  } catch (const std::exception &e) {
+    delete H;
+    return fail(DPGO_ERR_UNSUPPORTED, std::string("sparse exact preconditioner setup: ") + e.what());
+  }
+  if (plan.max_ytiles > dpgo::ND_YCAP_TILES || plan.max_slots > dpgo::ND_SLOT_CAP) {
+    delete H;
+    return fail(DPGO_ERR_UNSUPPORTED, "sparse exact preconditioner: plan exceeds the shared-memory capacities");
+  }
+  p->nd_H = H;
+  nd_fill_info(*H, plan, p->nd_info);
+  DPGO_TRY(upload_array(plan.phases, p->nd.phases, p->stream));
+  DPGO_TRY(upload_array(plan.cta_step, p->nd.cta_step, p->stream));
+  DPGO_TRY(upload_array(plan.steps, p->nd.steps, p->stream));
+  DPGO_TRY(upload_array(plan.gathers, p->nd.gathers, p->stream));
+  DPGO_TRY(upload_array(plan.jobs, p->nd.jobs, p->stream));
+  DPGO_TRY(upload_array(plan.epis, p->nd.epis, p->stream));
+  DPGO_TRY(upload_array(plan.csrc, p->nd.csrc, p->stream));
+  DPGO_TRY(upload_array(blob, p->nd.blob, p->stream));
+  const size_t tile = sizeof(double) * (size_t)p->ts;
+  DPGO_CUDA(cudaMalloc(&p->nd.TX, tile * (size_t)p->n));
+  DPGO_CUDA(cudaMalloc(&p->nd.C, tile * (size_t)H->cbuf_tiles));
+  DPGO_CUDA(cudaMemsetAsync(p->nd.TX, 0, tile * (size_t)p->n, p->stream));
+  DPGO_CUDA(cudaMemsetAsync(p->nd.C, 0, tile * (size_t)H->cbuf_tiles, p->stream));
+  DPGO_CUDA(cudaStreamSynchronize(p->stream));
+  p->nd.nphases = (int)plan.phases.size();
+  p->nd_ready = true;
+  return DPGO_OK;
+}
+
 int check_precond(dpgo_problem *p, int precond) {
-  if (precond < 0 || precond > 2) return fail(DPGO_ERR_INVALID_ARG, "unknown preconditioner id");
+  if (precond < 0 || precond > 3) return fail(DPGO_ERR_INVALID_ARG, "unknown preconditioner id");
+  if (precond == DPGO_PRECOND_SPARSE_EXACT) return ensure_nd(p);
   if (precond == DPGO_PRECOND_BLOCK_JACOBI && !p->d_dinv)
     return fail(DPGO_ERR_STATE, "block-Jacobi preconditioner was not prepared by set_Q (precond_mask)");
   if (precond == DPGO_PRECOND_DENSE_EXACT) return ensure_dense(p);
@@ -265,8 +369,9 @@ struct BlockTriplet {
   double v[16];        // padded 4x4, v[k*4+c] = Q[dh*brow+k, dh*bcol+c]
 };
 
-int build_from_triplets(dpgo_problem *p, std::vector<BlockTriplet> &trip, unsigned precond_mask) {
-  const int n = p->n, dh = p->dh;
+// block triplets -> block-CSR (rows = output tiles, duplicates summed in a fixed order)
+void assemble_bsr(int n, const std::vector<BlockTriplet> &trip, std::vector<int> &rowptr, std::vector<int> &bcol,
+                  std::vector<double> &bval) {
   // sort by (output tile = bcol, neighbour tile = brow); stable so duplicate summation order is fixed
   std::vector<int64_t> order(trip.size());
   std::iota(order.begin(), order.end(), 0);
@@ -274,8 +379,9 @@ int build_from_triplets(dpgo_problem *p, std::vector<BlockTriplet> &trip, unsign
     if (trip[x].bcol != trip[y].bcol) return trip[x].bcol < trip[y].bcol;
     return trip[x].brow < trip[y].brow;
   });
-  std::vector<int> rowptr(n + 1, 0), bcol;
-  std::vector<double> bval;
+  rowptr.assign((size_t)n + 1, 0);
+  bcol.clear();
+  bval.clear();
   bcol.reserve(trip.size());
   bval.reserve(trip.size() * 16);
   int last_j = -1, last_i = -1;
@@ -293,6 +399,13 @@ int build_from_triplets(dpgo_problem *p, std::vector<BlockTriplet> &trip, unsign
     }
   }
   for (int j = 0; j < n; ++j) rowptr[j + 1] += rowptr[j];
+}
+
+int build_from_triplets(dpgo_problem *p, std::vector<BlockTriplet> &trip, unsigned precond_mask) {
+  const int n = p->n, dh = p->dh;
+  std::vector<int> rowptr, bcol;
+  std::vector<double> bval;
+  assemble_bsr(n, trip, rowptr, bcol, bval);
   const int64_t nb = (int64_t)bcol.size();
 
   // block-Jacobi inverse blocks (Q_jj + 0.1 I)^-1, stored [k][c] padded
@@ -327,7 +440,7 @@ int build_from_triplets(dpgo_problem *p, std::vector<BlockTriplet> &trip, unsign
   const int sg = (p->r > 4) ? 32 : ((p->r > 2) ? 16 : 8);
   const int rows_per_pass = (dpgo::OPT_THREADS / 32) * (32 / sg);
   int grid = p->max_grid;
-  const bool dense = (precond_mask & (1u << DPGO_PRECOND_DENSE_EXACT)) != 0;
+  const bool dense = (precond_mask & ((1u << DPGO_PRECOND_DENSE_EXACT) | (1u << DPGO_PRECOND_SPARSE_EXACT))) != 0;
   if (!dense) grid = std::max(1, std::min(grid, (n + rows_per_pass - 1) / rows_per_pass));
   std::vector<int> cta_rows(grid + 1, 0);
   {
@@ -352,6 +465,10 @@ int build_from_triplets(dpgo_problem *p, std::vector<BlockTriplet> &trip, unsign
   p->sym_ok = 0;
   p->have_Q = false;
   p->ngroups = 0;
+  free_nd(p);
+  p->h_rowptr = rowptr;
+  p->h_bcol = bcol;
+  p->h_bval = bval;
   // +8 ints of slack: the bulk-TMA windows are rounded out to 16 bytes
   DPGO_CUDA(cudaMalloc(&p->d_rowptr, sizeof(int) * (n + 1 + 8)));
   DPGO_CUDA(cudaMalloc(&p->d_bcol, sizeof(int) * (std::max<int64_t>(nb, 1) + 8)));
@@ -423,11 +540,6 @@ int fetch_result(dpgo_problem *p) {
     cudaError_t _e = cudaSetDevice((p)->device);                                     \
     if (_e != cudaSuccess) return fail(DPGO_ERR_CUDA, cudaGetErrorString(_e));       \
   } while (0)
-#define DPGO_TRY(expr)            \
-  do {                            \
-    int _s = (expr);              \
-    if (_s != DPGO_OK) return _s; \
-  } while (0)
 
 }  // namespace
 
@@ -453,7 +565,7 @@ void dpgo_opt_params_default(dpgo_opt_params_t *p) {
   p->algorithm = DPGO_ALG_RTR;        // ref: src/QuadraticOptimizer.cpp:22-28
   p->tr_iterations = 1;
   p->tr_max_inner = 50;
-  p->precond = DPGO_PRECOND_DENSE_EXACT;
+  p->precond = DPGO_PRECOND_SPARSE_EXACT;
   p->rgd_stepsize = 1e-3;
   p->tr_tolerance = 1e-2;
   p->tr_initial_radius = 1e1;
@@ -520,6 +632,7 @@ int dpgo_problem_destroy(dpgo_problem_t *p) {
   free_dev(p->d_S[0]); free_dev(p->d_S[1]); free_dev(p->d_partials); free_dev(p->d_bar); free_dev(p->d_phase_ns); free_dev(p->d_result);
   free_dev(p->d_public); free_dev(p->d_pose_ids); free_dev(p->d_pose_ptr); free_dev(p->d_edge_slot);
   free_dev(p->d_edge_out); free_dev(p->d_edge_T); free_dev(p->d_edge_om);
+  free_nd(p);
   if (p->h_result) cudaFreeHost(p->h_result);
   if (p->own_stream) cudaStreamDestroy(p->own_stream);
   delete p;
@@ -912,11 +1025,62 @@ int64_t dpgo_precond_algorithmic_bytes(const dpgo_problem_t *p, int precondition
   if (!p) return 0;
   const int64_t N = (int64_t)p->dh * p->n, vec = (int64_t)p->r * N * 8;
   if (preconditioner == DPGO_PRECOND_BLOCK_JACOBI) return (int64_t)p->n * 16 * 8 + 2 * vec;
+  if (preconditioner == DPGO_PRECOND_SPARSE_EXACT) return p->nd_ready ? p->nd_info[4] + 2 * vec : 0;
   if (preconditioner != DPGO_PRECOND_DENSE_EXACT) return 0;
   // the inverse is symmetric: the unique data is its upper triangle in 8-row groups (what phase_dense_sym reads);
   // the full-matrix variants read all of it
   const int64_t mat = p->sym_ok ? (N * N + 8 * N) / 2 * 8 : N * N * 8;
   return mat + 2 * vec;
+}
+
+int dpgo_nd_info(dpgo_problem_t *p, int64_t *info16) {
+  DPGO_CHECK_HANDLE(p);
+  DPGO_REQUIRE(info16, DPGO_ERR_INVALID_ARG, "null argument");
+  DPGO_REQUIRE(p->have_Q, DPGO_ERR_STATE, "set_Q has not been called");
+  DPGO_TRY(ensure_nd(p));
+  std::copy(p->nd_info, p->nd_info + 16, info16);
+  return DPGO_OK;
+}
+
+int dpgo_nd_debug_emulate(int n, int d, int r, int64_t nb, const int32_t *brow, const int32_t *bcol, const double *blocks,
+                          double shift, int grid, int force_cuts, int leaf_size, const double *V_host, double *Z_host,
+                          int64_t *info16) {
+  DPGO_REQUIRE(n >= 1 && (d == 2 || d == 3) && r >= 1 && r <= 8 && grid >= 1, DPGO_ERR_INVALID_ARG, "bad dimensions");
+  DPGO_REQUIRE(nb >= 0 && (nb == 0 || (brow && bcol && blocks)) && V_host && Z_host, DPGO_ERR_INVALID_ARG, "null argument");
+  const int dh = d + 1;
+  std::vector<BlockTriplet> trip((size_t)nb);
+  for (int64_t q = 0; q < nb; ++q) {
+    if (brow[q] < 0 || brow[q] >= n || bcol[q] < 0 || bcol[q] >= n) return fail(DPGO_ERR_INVALID_ARG, "block index out of range");
+    trip[(size_t)q].brow = brow[q];
+    trip[(size_t)q].bcol = bcol[q];
+    std::memset(trip[(size_t)q].v, 0, sizeof(trip[(size_t)q].v));
+    for (int k = 0; k < dh; ++k)
+      for (int c = 0; c < dh; ++c) trip[(size_t)q].v[k * 4 + c] = blocks[(size_t)q * dh * dh + k * dh + c];
+  }
+  std::vector<int> rowptr, bc;
+  std::vector<double> bv;
+  assemble_bsr(n, trip, rowptr, bc, bv);
+  namespace nd = dpgo::nd;
+  try {
+    nd::Options opt = nd_options(grid, r);
+    opt.force_ncuts = force_cuts;
+    opt.shift = shift;
+    if (leaf_size > 0) opt.leaf_size = leaf_size;
+    nd::BsrView Q{n, dh, rowptr.data(), bc.data(), bv.data()};
+    nd::Hierarchy H;
+    nd::Plan plan;
+    std::vector<double> blob;
+    nd::build_hierarchy(Q, opt, H);
+    nd::build_numeric(Q, opt, H, blob);
+    nd::build_plan(H, opt, plan);
+    if (plan.max_ytiles > opt.ycap_tiles || plan.max_slots > opt.slot_cap)
+      return fail(DPGO_ERR_UNSUPPORTED, "plan exceeds the shared-memory capacities");
+    nd::emulate_apply(H, plan, blob, r, V_host, Z_host);
+    if (info16) nd_fill_info(H, plan, info16);
+  } catch (const std::exception &e) {
+    return fail(DPGO_ERR_UNSUPPORTED, std::string("sparse exact preconditioner: ") + e.what());
+  }
+  return DPGO_OK;
 }
 
 // ---- boundary-pose exchange --------------------------------------------------------------------

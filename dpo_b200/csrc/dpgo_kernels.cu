@@ -124,7 +124,7 @@ __device__ void phase_eval(const KParams &kp, int cb, bool save_xin, int precond
       double *s = S + (size_t)js * 9 + it.c * 3;
       s[0] = sym[0]; s[1] = sym[1]; s[2] = sym[2];
     }
-    if (precond != DPGO_PRECOND_DENSE_EXACT) {
+    if (precond != DPGO_PRECOND_DENSE_EXACT && precond != DPGO_PRECOND_SPARSE_EXACT) {
       double z0 = rg;
       if (precond == DPGO_PRECOND_BLOCK_JACOBI) {
         double t = jacobi_elem<R, DH>(kp.dinv, js, ld ? rg : 0.0, it.a, it.c);
@@ -227,7 +227,7 @@ __device__ void phase_update(const KParams &kp, int cb, const double *dcur, doub
       acc[0] = fma(res, res, acc[0]);
       x = __ldcg(X + idx);
     }
-    if (precond != DPGO_PRECOND_DENSE_EXACT) {
+    if (precond != DPGO_PRECOND_DENSE_EXACT && precond != DPGO_PRECOND_SPARSE_EXACT) {
       double z = res;
       if (precond == DPGO_PRECOND_BLOCK_JACOBI) {
         double t = jacobi_elem<R, DH>(kp.dinv, js, res, it.a, it.c);
@@ -685,6 +685,133 @@ __device__ void phase_pz(const KParams &kp, int cb, const double *V, double *Zou
 }
 
 // ---------------------------------------------------------------------------------------------
+// Sparse exact preconditioner (ref: QuadraticProblem::PreConditioner, src/QuadraticProblem.cpp:75-87 = CHOLMOD solve
+// with Q + 0.1 I, then projection).  One phase of the nested-dissection block solve (nd_precond.h): the CTA walks its
+// steps of the host-built plan:
+//   gathers   : tiles of the phase's input vector -> shared memory (forward: residual minus the children's
+//               contributions; backward: the ancestors' solution), one sub-group per tile
+//   jobs      : one warp = one 8-row panel x a column piece; lane (row = lane & 7, cp = lane >> 3) reads columns
+//               cp, cp + 4, ... : 256 contiguous bytes per warp load; r accumulators per lane; 2 shuffle steps
+//   epilogues : one sub-group per pose: sums the panel's partial slots in fixed order, writes t / contribution / x;
+//               solution tiles are projected onto the tangent space at X and dotted with V on the fly.
+// acc[0] accumulates <Z, V> over the phases of one application.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ int4 ld_int4(const void *p) { return __ldg(reinterpret_cast<const int4 *>(p)); }
+
+template <int R, int DH>
+__device__ void phase_nd(const KParams &kp, int ph, const double *V, int cb, double *Zout, double *ys, double *slots,
+                         double (&acc)[NRED]) {
+  constexpr int TS = R * DH;
+  constexpr int SG = SubGroup<R>::SG;
+  constexpr int SGW = 32 / SG;
+  constexpr int SLOT = nd::PANEL_ROWS * R;
+  const KNd &N = kp.nd;
+  const int4 P = ld_int4(N.phases + ph);                  // dir, stage, step_ptr0, pad
+  const int dir = P.x;
+  const int s0 = ld_const(N.cta_step + P.z + blockIdx.x), s1 = ld_const(N.cta_step + P.z + blockIdx.x + 1);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  const int sgw = lane / SG, l = lane & (SG - 1), a = l >> 2, c = l & 3;
+  const bool valid = (a < R) && (c < DH);
+  const int e = c * R + a;
+  const int nsub = nwarps * SGW, sub = warp * SGW + sgw;
+  const double *X = kp.v[V_X0 + cb];
+  const double *src = (dir == 0) ? V : N.TX;
+  for (int si = s0; si < s1; ++si) {
+    const int4 sa = ld_int4(N.steps + si), sb = ld_int4(reinterpret_cast<const int4 *>(N.steps + si) + 1);
+    const int g0 = sa.x, g1 = sa.y, j0 = sa.z, j1 = sa.w, e0 = sb.x, e1 = sb.y;
+    // ---- gathers ----
+    for (int gi = g0 + sub; gi < g1; gi += nsub) {
+      const int4 g = ld_int4(N.gathers + gi);             // ytile, src, c0, c1
+      if (valid) {
+        double v = __ldcg(src + (size_t)g.y * TS + e);
+        for (int k = g.z; k < g.w; ++k) v -= __ldcg(N.C + (size_t)ld_const(N.csrc + k) * TS + e);
+        ys[(size_t)g.x * TS + e] = v;
+      }
+    }
+    __syncthreads();
+    // ---- jobs ----
+    {
+      const int row = lane & 7, cp = lane >> 3;
+      for (int ji = j0 + warp; ji < j1; ji += nwarps) {
+        const int4 ja = ld_int4(N.jobs + ji), jb = ld_int4(reinterpret_cast<const int4 *>(N.jobs + ji) + 1);
+        const long long mat = ((long long)(unsigned)ja.x) | ((long long)ja.y << 32);
+        const int ncols = ja.z, ycol = ja.w, slot = jb.x, accum = jb.y;
+        const double *mp = N.blob + mat + row;
+        const double *yp = ys + (size_t)ycol * R;
+        double av[R];
+#pragma unroll
+        for (int q = 0; q < R; ++q) av[q] = 0.0;
+        int j = cp;
+        for (; j + 28 < ncols; j += 32) {
+          double m[8];
+#pragma unroll
+          for (int u = 0; u < 8; ++u) m[u] = ld_stream(mp + (size_t)(j + 4 * u) * nd::PANEL_ROWS);
+#pragma unroll
+          for (int u = 0; u < 8; ++u) {
+            const double *y = yp + (size_t)(j + 4 * u) * R;
+#pragma unroll
+            for (int q = 0; q < R; ++q) av[q] = fma(m[u], y[q], av[q]);
+          }
+        }
+        for (; j < ncols; j += 4) {
+          const double m = ld_stream(mp + (size_t)j * nd::PANEL_ROWS);
+          const double *y = yp + (size_t)j * R;
+#pragma unroll
+          for (int q = 0; q < R; ++q) av[q] = fma(m, y[q], av[q]);
+        }
+#pragma unroll
+        for (int q = 0; q < R; ++q) {
+          av[q] += shfl_xor(av[q], 8);
+          av[q] += shfl_xor(av[q], 16);
+        }
+        if (cp == 0) {
+          double *sl = slots + (size_t)slot * SLOT + row * R;
+#pragma unroll
+          for (int q = 0; q < R; ++q) sl[q] = accum ? sl[q] + av[q] : av[q];
+        }
+      }
+    }
+    __syncthreads();
+    // ---- epilogues (warp-uniform trip count: the projection uses full-warp shuffles) ----
+    for (int eb = e0 + warp * SGW; eb < e1; eb += nsub) {
+      const int ei = eb + sgw;
+      const bool act = (ei < e1);
+      int4 ea = make_int4(-1, 0, 0, 0), ec = make_int4(0, 0, 0, 0);
+      if (act) { ea = ld_int4(N.epis + ei); ec = ld_int4(reinterpret_cast<const int4 *>(N.epis + ei) + 1); }
+      const int kind = ea.x, slot0 = ea.y, nslots = ea.z, half = ea.w, out = ec.x, aux = ec.y, c0 = ec.z, c1 = ec.w;
+      const bool ld = act && valid;
+      double sum = 0.0;
+      if (ld) {
+        const double *sl = slots + (size_t)slot0 * SLOT + (half * DH + c) * R + a;
+        for (int k = 0; k < nslots; ++k) sum += sl[(size_t)k * SLOT];
+      }
+      const bool sol = (kind == nd::EPI_ROOT) || (kind == nd::EPI_B_OWN);
+      double x = 0.0, xq = 0.0;
+      if (ld) {
+        if (kind == nd::EPI_F_OWN) {
+          N.TX[(size_t)out * TS + e] = sum;
+        } else if (kind == nd::EPI_F_BND) {
+          for (int k = c0; k < c1; ++k) sum += __ldcg(N.C + (size_t)ld_const(N.csrc + k) * TS + e);
+          N.C[(size_t)out * TS + e] = sum;
+        } else if (sol) {
+          x = (kind == nd::EPI_ROOT) ? sum : __ldcg(N.TX + (size_t)out * TS + e) - sum;
+          N.TX[(size_t)out * TS + e] = x;
+          xq = __ldcg(X + (size_t)aux * TS + e);
+        }
+      }
+      double ya[3], sym[3];
+      const double z = tangent_project_elem<R, DH>(xq, x, a, c, ya, sym);
+      if (ld && sol) {
+        Zout[(size_t)aux * TS + e] = z;
+        acc[0] = fma(z, __ldcg(V + (size_t)aux * TS + e), acc[0]);
+      }
+    }
+    // the next step's gathers / jobs rewrite ys / slots only after every warp is past its epilogues
+    if (si + 1 < s1) __syncthreads();
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // Phase RT: candidate X' = R_X(eta_final) with eta_final = eta + tau * delta (tau = 0 unless tCG
 // stopped on the trust-region boundary / negative curvature), and the model-decrease dots
 //   acc[0] = <eta, g>, acc[1] = <eta, H eta> with H eta = (res - g) + tau * HD (tCG recurrences).
@@ -805,7 +932,32 @@ template <int R, int DH> __global__ void __launch_bounds__(OPT_THREADS, 1) k_opt
   tick(-1);
   const dpgo_opt_params_t prm = kp.prm;
   const int precond = prm.precond;
+  const bool exact = (precond == DPGO_PRECOND_DENSE_EXACT) || (precond == DPGO_PRECOND_SPARSE_EXACT);
   double acc[NRED];
+  // sparse exact preconditioner: shared memory = gathered input tiles + partial-sum slots (aliases the dense ring)
+  double *nd_ys = sV;
+  double *nd_slots = sV + (size_t)ND_YCAP_TILES * R * DH;
+  // Z = P_X( (Q + 0.1 I)^-1 V ), returns <Z, V> in acc[0]; every phase ends with a grid barrier
+  auto apply_exact = [&](const double *Vv, int cbx, double *Zout) {
+    if (precond == DPGO_PRECOND_SPARSE_EXACT) {
+      zero(acc);
+      for (int ph = 0; ph < kp.nd.nphases; ++ph) {
+        phase_nd<R, DH>(kp, ph, Vv, cbx, Zout, nd_ys, nd_slots, acc);
+        if (ph + 1 < kp.nd.nphases) phase_end<0>(kp, bc, acc);
+      }
+      phase_end<1>(kp, bc, acc);
+      tick(1);
+    } else {
+      if (dense_sym) phase_dense_sym<R>(kp, Vv, ring, sV, sMeta);
+      else if (dense_tma) phase_dense_tma<R>(kp, Vv, sV, ring);
+      else phase_dense<R>(kp, Vv, sV);
+      zero(acc); phase_end<0>(kp, bc, acc);
+      tick(1);
+      zero(acc); phase_pz<R, DH>(kp, cbx, Vv, Zout, sV, acc);
+      phase_end<1>(kp, bc, acc);
+      tick(2);
+    }
+  };
   dpgo_opt_result_t res;
   res.success = 0; res.tcg_status = DPGO_TCG_NOT_RUN; res.tcg_iterations = 0; res.outer_iterations = 0;
   res.rejections = 0; res.spmv_passes = 0; res.precond_applies = 0; res.reserved0 = 0;
@@ -821,13 +973,8 @@ template <int R, int DH> __global__ void __launch_bounds__(OPT_THREADS, 1) k_opt
     return;
   }
   if (kp.op == OP_PRECON) {
-    if (precond == DPGO_PRECOND_DENSE_EXACT) {
-      if (dense_sym) phase_dense_sym<R>(kp, kp.v[V_AUX], ring, sV, sMeta);
-      else if (dense_tma) phase_dense_tma<R>(kp, kp.v[V_AUX], sV, ring);
-      else phase_dense<R>(kp, kp.v[V_AUX], sV);
-      zero(acc); phase_end<0>(kp, bc, acc);
-      zero(acc); phase_pz<R, DH>(kp, 0, kp.v[V_AUX], kp.v[V_Z], sV, acc);
-      phase_end<1>(kp, bc, acc);
+    if (exact) {
+      apply_exact(kp.v[V_AUX], 0, kp.v[V_Z]);
     } else {
       // reuse phase_update with res := AUX (first = false, alpha = 0 would need RES); do it directly
       constexpr int TS = R * DH;
@@ -909,19 +1056,12 @@ template <int R, int DH> __global__ void __launch_bounds__(OPT_THREADS, 1) k_opt
     const double Delta_max = single ? Delta : 5.0 * prm.tr_initial_radius;   // ref :80-81,:96-97
     int total_steps = 0;
     int cb = 0;                      // base buffer
-    bool z0_valid = (precond != DPGO_PRECOND_DENSE_EXACT);
+    bool z0_valid = !exact;
     int iter = 0;
     while (true) {
       // -- z0 = M^-1 g for the dense preconditioner (pose-local ones were fused into phase E)
       if (!z0_valid) {
-        if (dense_sym) phase_dense_sym<R>(kp, kp.v[V_RG0 + cb], ring, sV, sMeta);
-        else if (dense_tma) phase_dense_tma<R>(kp, kp.v[V_RG0 + cb], sV, ring);
-        else phase_dense<R>(kp, kp.v[V_RG0 + cb], sV);
-        zero(acc); phase_end<0>(kp, bc, acc);
-        tick(1);
-        zero(acc); phase_pz<R, DH>(kp, cb, kp.v[V_RG0 + cb], kp.v[V_Z00 + cb], sV, acc);
-        phase_end<1>(kp, bc, acc);
-        tick(2);
+        apply_exact(kp.v[V_RG0 + cb], cb, kp.v[V_Z00 + cb]);
         zr0 = acc[0];
         z0_valid = true;
       }
@@ -966,15 +1106,8 @@ template <int R, int DH> __global__ void __launch_bounds__(OPT_THREADS, 1) k_opt
           break;
         }
         double zr_new = acc[1];
-        if (precond == DPGO_PRECOND_DENSE_EXACT) {
-          if (dense_sym) phase_dense_sym<R>(kp, kp.v[V_RES], ring, sV, sMeta);
-          else if (dense_tma) phase_dense_tma<R>(kp, kp.v[V_RES], sV, ring);
-          else phase_dense<R>(kp, kp.v[V_RES], sV);
-          zero(acc); phase_end<0>(kp, bc, acc);
-          tick(1);
-          zero(acc); phase_pz<R, DH>(kp, cb, kp.v[V_RES], kp.v[V_Z], sV, acc);
-          phase_end<1>(kp, bc, acc);
-          tick(2);
+        if (exact) {
+          apply_exact(kp.v[V_RES], cb, kp.v[V_Z]);
           zr_new = acc[0];
         }
         res.precond_applies++;
@@ -1018,7 +1151,7 @@ template <int R, int DH> __global__ void __launch_bounds__(OPT_THREADS, 1) k_opt
         if (accepted) {
           cb = 1 - cb; f1 = f2; gn = gn2; zr0 = acc[3];
           res.f_opt = f2; res.gradnorm_opt = gn2;
-          z0_valid = (precond != DPGO_PRECOND_DENSE_EXACT);
+          z0_valid = !exact;
         } else {
           res.rejections++;
         }

@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include "../../include/dpgo_b200.h"
+#include "nd_precond.h"
 
 namespace dpgo {
 
@@ -33,7 +34,24 @@ enum OpCode {
 constexpr int NRED = 4;            // scalars reduced per phase
 constexpr int OPT_THREADS = 512;   // persistent kernel block size
 constexpr int SPMV_GROUP_BLOCKS = 192;  // blocks per row group of the TMA-fed SpMV (24 KB of Q per smem stage)
+constexpr int ND_YCAP_TILES = 600;  // sparse exact preconditioner: pose tiles of a phase's input vector staged in shared memory per step
+constexpr int ND_SLOT_CAP = 240;    // ... and partial-sum slots (8 rows x r doubles) per step
 constexpr int DENSE_PER_MAX = 512;  // max rows of the dense inverse one CTA owns (smem staging of V): N <= 75k at 148 CTAs
+
+// sparse exact preconditioner (nd_precond.h): the static plan and the panel blob in HBM / L2
+struct KNd {
+  int nphases;
+  const nd::Phase *phases;
+  const int *cta_step;
+  const nd::Step *steps;
+  const nd::Gather *gathers;
+  const nd::Job *jobs;
+  const nd::Epi *epis;
+  const int *csrc;
+  const double *blob;
+  double *TX;            // n tiles, permuted order: t (forward) then x (backward), unprojected
+  double *C;             // contribution tiles of the forward sweep
+};
 
 struct KParams {
   int n;                 // poses
@@ -64,6 +82,7 @@ struct KParams {
   unsigned *bar_epoch;
   dpgo_opt_params_t prm;
   dpgo_opt_result_t *result;   // device copy of the result record
+  KNd nd;                // sparse exact preconditioner (nd.nphases == 0: not prepared)
   unsigned long long *phase_ns; // diagnostic (nullable): per phase kind, ns seen by CTA 0 (dpgo_debug_phase_times)
 };
 

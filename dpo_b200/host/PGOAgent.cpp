@@ -151,7 +151,8 @@ void PGOAgent::setPoseGraph(const std::vector<RelativeSEMeasurement> &inputOdome
   }
   delete mProblemPtr;
   mProblemPtr = new QuadraticProblem(num_poses(), dimension(), relaxation_rank());
-  mProblemPtr->setPreconditioners(true, mParams.preconditioner == Preconditioner::DenseExact);
+  mProblemPtr->setPreconditioners(true, mParams.preconditioner == Preconditioner::DenseExact || mParams.preconditioner == Preconditioner::SparseExact,
+                                  mParams.preconditioner);
   constructQMatrix();               // Q does not depend on the neighbours
   if (!local_init) {
     if (mParams.verbose) printf("Using provided trajectory initialization.\n");
@@ -614,7 +615,8 @@ Matrix PGOAgent::localPoseGraphOptimization() {
   if (!TLocalInit) localInitialization();
   SparseMatrix Q = constructConnectionLaplacianSE(concat(odometry, privateLoopClosures));
   QuadraticProblem problem(n, d, d);        // rank r = d
-  problem.setPreconditioners(true, mParams.preconditioner == Preconditioner::DenseExact);
+  problem.setPreconditioners(true, mParams.preconditioner == Preconditioner::DenseExact || mParams.preconditioner == Preconditioner::SparseExact,
+                             mParams.preconditioner);
   problem.setQ(Q);
   QuadraticOptimizer optimizer(&problem);
   optimizer.setVerbose(mParams.verbose);

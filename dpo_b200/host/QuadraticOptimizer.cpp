@@ -10,7 +10,7 @@
 namespace DPGO {
 
 QuadraticOptimizer::QuadraticOptimizer(QuadraticProblem *p)
-    : problem(p), algorithm(ROPTALG::RTR), preconditioner(Preconditioner::DenseExact), gradientDescentStepsize(1e-3),
+    : problem(p), algorithm(ROPTALG::RTR), preconditioner(Preconditioner::SparseExact), gradientDescentStepsize(1e-3),
       trustRegionTolerance(1e-2), trustRegionInitialRadius(1e1), trustRegionIterations(1),
       trustRegionMaxInnerIterations(50), verbose(false) {
   result.success = false;

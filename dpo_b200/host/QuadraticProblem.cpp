@@ -24,7 +24,7 @@ int QuadraticProblem::defaultDevice() {
 QuadraticProblem::QuadraticProblem(size_t nIn, size_t dIn, size_t rIn)
     : n(nIn), d(dIn), r(rIn), mQ((Eigen::Index)((dIn + 1) * nIn), (Eigen::Index)((dIn + 1) * nIn)),
       mG((Eigen::Index)rIn, (Eigen::Index)((dIn + 1) * nIn)), mDevice(defaultDevice()),
-      mPrecondMask((1u << DPGO_PRECOND_BLOCK_JACOBI) | (1u << DPGO_PRECOND_DENSE_EXACT)) {
+      mPrecondMask((1u << DPGO_PRECOND_BLOCK_JACOBI) | (1u << DPGO_PRECOND_SPARSE_EXACT)) {
   assert(r >= d);
 }
 
@@ -42,8 +42,9 @@ void QuadraticProblem::setDevice(int device) {
   mDevice = device;
 }
 
-void QuadraticProblem::setPreconditioners(bool blockJacobi, bool denseExact) {
-  mPrecondMask = (blockJacobi ? (1u << DPGO_PRECOND_BLOCK_JACOBI) : 0u) | (denseExact ? (1u << DPGO_PRECOND_DENSE_EXACT) : 0u);
+void QuadraticProblem::setPreconditioners(bool blockJacobi, bool exact, Preconditioner exactKind) {
+  const unsigned exactBit = (exactKind == Preconditioner::DenseExact) ? (1u << DPGO_PRECOND_DENSE_EXACT) : (1u << DPGO_PRECOND_SPARSE_EXACT);
+  mPrecondMask = (blockJacobi ? (1u << DPGO_PRECOND_BLOCK_JACOBI) : 0u) | (exact ? exactBit : 0u);
   if (mHandle && mQ.nonZeros() > 0) setQ(SparseMatrix(mQ));
 }
 
@@ -115,7 +116,8 @@ Matrix QuadraticProblem::RieHessianEta(const Matrix &Y, const Matrix &Vin) const
 Matrix QuadraticProblem::PreConditioner(const Matrix &Y, const Matrix &Vin) const {
   ensureHandle();
   Matrix out((Eigen::Index)r, (Eigen::Index)((d + 1) * n));
-  const int which = (mPrecondMask & (1u << DPGO_PRECOND_DENSE_EXACT)) ? DPGO_PRECOND_DENSE_EXACT : DPGO_PRECOND_BLOCK_JACOBI;
+  const int which = (mPrecondMask & (1u << DPGO_PRECOND_SPARSE_EXACT)) ? DPGO_PRECOND_SPARSE_EXACT
+                    : (mPrecondMask & (1u << DPGO_PRECOND_DENSE_EXACT)) ? DPGO_PRECOND_DENSE_EXACT : DPGO_PRECOND_BLOCK_JACOBI;
   if (dpgo_problem_precon(mHandle, which, Y.data(), Vin.data(), out.data()) != DPGO_OK) {
     printf("Preconditioner failed.\n");      // ref :83-86: fall back to the identity
     return Vin;

@@ -14,8 +14,8 @@ from typing import Optional
 import numpy as np
 
 from . import _capi as capi
-from ._capi import (ALG_RGD, ALG_RTR, PRECOND_BLOCK_JACOBI, PRECOND_DENSE_EXACT, PRECOND_NONE, OptParams,
-                    OptResult)
+from ._capi import (ALG_RGD, ALG_RTR, PRECOND_BLOCK_JACOBI, PRECOND_DENSE_EXACT, PRECOND_NONE, PRECOND_SPARSE_EXACT,
+                    OptParams, OptResult)
 
 
 class ROPTALG:
@@ -31,7 +31,7 @@ class QuadraticProblem:
     """
 
     def __init__(self, n: int, d: int, r: int, device: int = 0,
-                 preconditioners=(PRECOND_BLOCK_JACOBI, PRECOND_DENSE_EXACT)):
+                 preconditioners=(PRECOND_BLOCK_JACOBI, PRECOND_SPARSE_EXACT)):
         self._lib = capi.load_library()
         self.n, self.d, self.r = int(n), int(d), int(r)
         self.N = (self.d + 1) * self.n
@@ -158,7 +158,7 @@ class QuadraticProblem:
         capi.check(self._lib.dpgo_problem_rhess(self._h, capi.dptr(Xf), capi.dptr(Vf), capi.dptr(out)))
         return out
 
-    def PreConditioner(self, X, V, precond: int = PRECOND_DENSE_EXACT) -> np.ndarray:
+    def PreConditioner(self, X, V, precond: int = PRECOND_SPARSE_EXACT) -> np.ndarray:
         Xf, Vf, out = self._in(X), self._in(V), self._out()
         capi.check(self._lib.dpgo_problem_precon(self._h, precond, capi.dptr(Xf), capi.dptr(Vf), capi.dptr(out)))
         return out
@@ -223,6 +223,14 @@ class QuadraticProblem:
     def spmv_algorithmic_bytes(self, add_G: bool = False) -> int:
         return int(self._lib.dpgo_spmv_algorithmic_bytes(self._h, int(add_G)))
 
+    def nd_info(self) -> dict:
+        """Diagnostics of the sparse exact preconditioner's hierarchy (prepares it if needed)."""
+        info = (C.c_int64 * 16)()
+        capi.check(self._lib.dpgo_nd_info(self._h, info))
+        keys = ("levels", "nodes", "phases", "block_bytes", "bytes_per_apply", "max_own", "max_bnd", "nd_depth", "steps",
+                "jobs", "epilogues", "max_ytiles", "max_slots")
+        return {k: int(info[i]) for i, k in enumerate(keys)}
+
     def precond_algorithmic_bytes(self, preconditioner: int) -> int:
         return int(self._lib.dpgo_precond_algorithmic_bytes(self._h, int(preconditioner)))
 
@@ -268,7 +276,8 @@ class QuadraticOptimizer:
         self._p.tr_max_inner = int(it)
 
     def setPreconditioner(self, precond: int) -> None:
-        """B200 extension: DENSE_EXACT (reference operator) | BLOCK_JACOBI (throughput) | NONE."""
+        """B200 extension: SPARSE_EXACT (reference operator, nested-dissection block solve; default) |
+        DENSE_EXACT (same operator through a dense inverse, A/B) | BLOCK_JACOBI (throughput) | NONE."""
         self._p.precond = int(precond)
 
     def params(self) -> OptParams:

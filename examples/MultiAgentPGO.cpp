@@ -86,7 +86,7 @@ int main(int argc, char **argv) {
     PGOAgentParameters prm(d, r, K);
     prm.acceleration = opt.accel;
     prm.algorithm = opt.rgd ? ROPTALG::RGD : ROPTALG::RTR;
-    prm.preconditioner = opt.jacobi ? Preconditioner::BlockJacobi : Preconditioner::DenseExact;
+    prm.preconditioner = opt.jacobi ? Preconditioner::BlockJacobi : Preconditioner::SparseExact;
     agents.emplace_back(new PGOAgent(a, prm));
     if (a > 0) {
       Matrix lift;

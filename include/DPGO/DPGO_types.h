@@ -32,7 +32,9 @@ typedef Eigen::SparseMatrix<double, Eigen::RowMajor> SparseMatrix;
 enum ROPTALG { RTR, RGD };
 
 // B200 extension: which operator truncated CG is preconditioned with (see include/dpgo_b200.h)
-enum class Preconditioner { None = 0, BlockJacobi = 1, DenseExact = 2 };
+// SparseExact = the reference's operator (Q + 0.1 I)^-1 through a nested-dissection block factorisation (default);
+// DenseExact = the same operator through a dense inverse (A/B runs)
+enum class Preconditioner { None = 0, BlockJacobi = 1, DenseExact = 2, SparseExact = 3 };
 
 // statistics of one QuadraticOptimizer::optimize() call
 struct ROPTResult {

@@ -55,7 +55,7 @@ struct PGOAgentParameters {
   bool verbose;
   bool logData;
   std::string logDirectory;
-  Preconditioner preconditioner = Preconditioner::DenseExact;   // B200 extension
+  Preconditioner preconditioner = Preconditioner::SparseExact;   // B200 extension
 
   PGOAgentParameters(unsigned dIn, unsigned rIn, unsigned numRobotsIn = 1, ROPTALG algorithmIn = ROPTALG::RTR,
                      bool accel = false, unsigned restartInt = 30, RobustCostType costType = RobustCostType::L2,

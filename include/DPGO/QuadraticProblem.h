@@ -39,7 +39,7 @@ class QuadraticProblem {
 
   // B200 extensions
   void setDevice(int device);                           // before the first setQ; default: env DPGO_DEVICE or 0
-  void setPreconditioners(bool blockJacobi, bool denseExact);
+  void setPreconditioners(bool blockJacobi, bool exact, Preconditioner exactKind = Preconditioner::SparseExact);
   dpgo_problem *handle() const { return mHandle; }
   static int defaultDevice();
 

@@ -59,8 +59,11 @@ enum { DPGO_ALG_RTR = 0, DPGO_ALG_RGD = 1 };
  * ref: src/QuadraticProblem.cpp:31-42,75-87: exact solve with Q + 0.1 I (CHOLMOD) followed by
  * tangent projection.  DENSE_EXACT applies the same operator through a dense inverse resident
  * in HBM (per-iteration trace parity with the reference); BLOCK_JACOBI is the SpMV-only
- * throughput mode (same fixed points, different inner iterates); NONE is projection only. */
-enum { DPGO_PRECOND_NONE = 0, DPGO_PRECOND_BLOCK_JACOBI = 1, DPGO_PRECOND_DENSE_EXACT = 2 };
+ * throughput mode (same fixed points, different inner iterates); NONE is projection only.
+ * SPARSE_EXACT applies the same operator as DENSE_EXACT through a nested-dissection block factorisation (dense
+ * Schur-complement blocks on 2-4 macro levels, L2-resident for sphere2500-sized agents; O(n log n)-ish memory instead
+ * of O(n^2)): the default, and what "exact" means everywhere below. */
+enum { DPGO_PRECOND_NONE = 0, DPGO_PRECOND_BLOCK_JACOBI = 1, DPGO_PRECOND_DENSE_EXACT = 2, DPGO_PRECOND_SPARSE_EXACT = 3 };
 
 /* ref: ROPTLIB tCGstatusSet as recorded by src/QuadraticOptimizer.cpp:115 */
 enum {
@@ -195,6 +198,18 @@ DPGO_API int64_t dpgo_precond_algorithmic_bytes(const dpgo_problem_t *p, int pre
 DPGO_API int dpgo_sym_plan_sizes(int N, int *num_segments, int *num_chunks);
 DPGO_API int dpgo_sym_plan(int N, int grid, double chunk_cost, int32_t *segptr, int32_t *cut, int32_t *cfirst,
                            int32_t *ccount, int64_t *chunk_offset);
+/* ---- sparse exact preconditioner: diagnostics ------------------------------------------------------------------ */
+/* info[16] of the prepared hierarchy (prepares it if needed): 0 macro levels, 1 macro nodes, 2 phases per application,
+ * 3 bytes of all blocks, 4 matrix bytes streamed per application, 5 largest own block (scalars), 6 largest boundary
+ * (scalars), 7 dissection depth, 8 steps, 9 jobs, 10 epilogues, 11.. reserved */
+DPGO_API int dpgo_nd_info(dpgo_problem_t *p, int64_t *info16);
+/* HOST ONLY, verification of the planning code on machines without a GPU (never used by a product path): builds the
+ * hierarchy, the blocks and the phase plan for the block matrix given as in dpgo_problem_set_Q_blocks and runs a host
+ * emulation of the plan exactly as the kernel interprets it:  Z = (Q + shift I)^-1 V  (no projection), V and Z
+ * r x (d+1)n column-major.  force_cuts < 0 lets the cost model choose the macro levels.  info16 as in dpgo_nd_info. */
+DPGO_API int dpgo_nd_debug_emulate(int n, int d, int r, int64_t nb, const int32_t *brow, const int32_t *bcol,
+                                   const double *blocks, double shift, int grid, int force_cuts, int leaf_size,
+                                   const double *V_host, double *Z_host, int64_t *info16);
 /* diagnostic: cost of one empty phase of the persistent kernel (grid barrier + scalar reduction) and of its launch */
 DPGO_API int dpgo_debug_phase_latency(dpgo_problem_t *p, int phases, double *us_per_phase, double *us_launch);
 /* diagnostic: phase clock of the persistent kernel.  enable != 0 switches it on (subsequent optimise calls

@@ -27,7 +27,7 @@ def make_problem(ds, r, data_dir, with_G=True, seed=0):
     op = orc.QuadraticProblem(n, d, r)
     op.set_Q(Q)
     op.set_G(G)
-    gp = dp.QuadraticProblem(n, d, r)
+    gp = dp.QuadraticProblem(n, d, r, preconditioners=(dp.PRECOND_BLOCK_JACOBI, dp.PRECOND_SPARSE_EXACT, dp.PRECOND_DENSE_EXACT))
     gp.setQ(Q)
     gp.setG(G)
     return op, gp, X, rng
@@ -82,7 +82,8 @@ def test_preconditioners(ds, r, data_dir):
     op, gp, X, rng = make_problem(ds, r, data_dir, with_G=False)
     V = rng.standard_normal(X.shape)
     exact = op.precondition(X, V)
-    assert relerr(gp.PreConditioner(X, V, dp.PRECOND_DENSE_EXACT), exact) <= 1e-9
+    assert relerr(gp.PreConditioner(X, V, dp.PRECOND_SPARSE_EXACT), exact) <= 1e-11      # nested-dissection block solve (default)
+    assert relerr(gp.PreConditioner(X, V, dp.PRECOND_DENSE_EXACT), exact) <= 1e-9        # dense inverse (A/B)
     oo = orc.QuadraticOptimizer(op, precond="jacobi")
     assert relerr(gp.PreConditioner(X, V, dp.PRECOND_BLOCK_JACOBI), oo._apply_precond(X, V)) <= 1e-12
     assert relerr(gp.PreConditioner(X, V, dp.PRECOND_NONE), orc.tangent_project(X, V, op.d)) <= 1e-13

@@ -48,14 +48,17 @@ def test_rgd_step(ds, r, data_dir):
         assert abs(res.relative_change - oo.result.relativeChange) <= 1e-9 * oo.result.relativeChange
 
 
-@pytest.mark.parametrize("precond", ["exact", "jacobi", "none"])
+@pytest.mark.parametrize("precond", ["exact", "dense", "jacobi", "none"])
 @pytest.mark.parametrize("ds,r", [("tinyGrid3D", 3), ("smallGrid3D", 5), ("sphere2500", 5), ("sphere2500", 3),
                                   ("CSAIL", 5)])
 def test_rtr_single_step_sequence(ds, r, precond, data_dir):
     """updateX constants (ref src/PGOAgent.cpp:1131-1137): tol 1e-2, 1 outer, <=10 inner, radius 100."""
     import dpo_b200 as dp
-    pid = {"exact": dp.PRECOND_DENSE_EXACT, "jacobi": dp.PRECOND_BLOCK_JACOBI, "none": dp.PRECOND_NONE}[precond]
-    op, gp, X0 = setup(ds, r, data_dir)
+    # "exact" = the default nested-dissection block solve, "dense" = the same operator through the dense inverse
+    pid = {"exact": dp.PRECOND_SPARSE_EXACT, "dense": dp.PRECOND_DENSE_EXACT, "jacobi": dp.PRECOND_BLOCK_JACOBI,
+           "none": dp.PRECOND_NONE}[precond]
+    op, gp, X0 = setup(ds, r, data_dir, precs=(dp.PRECOND_BLOCK_JACOBI, pid) if pid else None)
+    precond = "exact" if precond == "dense" else precond
     Xo, Xg = X0, X0
     # un-/weakly preconditioned CG amplifies summation-order differences between the two implementations
     tol, ftol = (1e-8, 1e-9) if precond == "exact" else ((1e-9, 1e-9) if precond == "jacobi" else (1e-5, 1e-7))
