@@ -91,6 +91,8 @@ SIGNATURES = {
                                         C.c_int, _dp, _dp, C.POINTER(C.c_int64)]),
     "dpgo_debug_phase_latency": (C.c_int, [_vp, C.c_int, _dp, _dp]),
     "dpgo_debug_phase_times": (C.c_int, [_vp, C.c_int, _dp]),
+    "dpgo_debug_phase_times32": (C.c_int, [_vp, C.c_int, _dp]),
+    "dpgo_debug_phase_times64": (C.c_int, [_vp, C.c_int, _dp]),
     "dpgo_agent_set_public_poses": (C.c_int, [_vp, C.c_int, _ip]),
     "dpgo_agent_pack_public": (C.c_int, [_vp, _vp]),
     "dpgo_agent_set_shared_edges": (C.c_int, [_vp, C.c_int, _ip, _ip, _ip, _dp, _dp]),

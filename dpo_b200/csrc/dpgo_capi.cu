@@ -125,6 +125,9 @@ void fill_kparams(const dpgo_problem *p, dpgo::KParams &kp, int op, const dpgo_o
   kp.bar_epoch = p->d_bar + 1;
   kp.nd = p->nd;
   if (!p->nd_ready) kp.nd.nphases = 0;
+  static const int strict = [] { const char *e = std::getenv("DPGO_STRICT_ACQUIRE"); return (e && e[0] == '1') ? 1 : 0; }();
+  kp.strict_acquire = strict;
+  kp.smem_doubles = 0;
   kp.phase_ns = p->d_phase_ns;
   kp.prm = prm;
   kp.result = p->d_result;
@@ -292,7 +295,7 @@ template <class T> int upload_array(const std::vector<T> &h, const T *&d, cudaSt
 
 void free_nd(dpgo_problem *p) {
   auto fr = [](const void *q) { if (q) cudaFree(const_cast<void *>(q)); };
-  fr(p->nd.phases); fr(p->nd.cta_step); fr(p->nd.steps); fr(p->nd.gathers); fr(p->nd.jobs); fr(p->nd.epis); fr(p->nd.csrc);
+  fr(p->nd.cta_phase); fr(p->nd.steps); fr(p->nd.gathers); fr(p->nd.jobs); fr(p->nd.epis); fr(p->nd.csrc);
   fr(p->nd.blob); fr(p->nd.TX); fr(p->nd.C);
   p->nd = dpgo::KNd();
   delete p->nd_H;
@@ -327,8 +330,16 @@ int ensure_nd(dpgo_problem *p) {
   }
   p->nd_H = H;
   nd_fill_info(*H, plan, p->nd_info);
-  DPGO_TRY(upload_array(plan.phases, p->nd.phases, p->stream));
-  DPGO_TRY(upload_array(plan.cta_step, p->nd.cta_step, p->stream));
+  if ((int)plan.phases.size() > dpgo::nd::MAX_PHASES) {
+    delete H;
+    p->nd_H = nullptr;
+    return fail(DPGO_ERR_UNSUPPORTED, "sparse exact preconditioner: too many phases");
+  }
+  for (size_t k = 0; k < plan.phases.size(); ++k) { p->nd.dir[k] = plan.phases[k].dir; p->nd.cta0[k] = plan.phases[k].cta0; }
+  p->nd.max_ytiles = std::max(plan.max_ytiles, 1);
+  p->nd.max_slots = std::max(plan.max_slots, 1);
+  p->nd.max_gathers = p->nd.max_ytiles;          // a step gathers at most what its shared-memory tiles hold
+  DPGO_TRY(upload_array(plan.cta_phase, p->nd.cta_phase, p->stream));
   DPGO_TRY(upload_array(plan.steps, p->nd.steps, p->stream));
   DPGO_TRY(upload_array(plan.gathers, p->nd.gathers, p->stream));
   DPGO_TRY(upload_array(plan.jobs, p->nd.jobs, p->stream));
@@ -959,25 +970,29 @@ int dpgo_debug_phase_latency(dpgo_problem_t *p, int phases, double *us_per_phase
   return DPGO_OK;
 }
 
-int dpgo_debug_phase_times(dpgo_problem_t *p, int enable, double *ms_by_kind) {
+static int phase_times_impl(dpgo_problem_t *p, int enable, double *ms_by_kind, int nout) {
   DPGO_CHECK_HANDLE(p);
   if (enable && !p->d_phase_ns) {
-    DPGO_CUDA(cudaMalloc(&p->d_phase_ns, 8 * sizeof(unsigned long long)));
-    DPGO_CUDA(cudaMemsetAsync(p->d_phase_ns, 0, 8 * sizeof(unsigned long long), p->stream));
+    DPGO_CUDA(cudaMalloc(&p->d_phase_ns, 64 * sizeof(unsigned long long)));
+    DPGO_CUDA(cudaMemsetAsync(p->d_phase_ns, 0, 64 * sizeof(unsigned long long), p->stream));
   }
   if (p->d_phase_ns) {
-    unsigned long long ns[8];
+    unsigned long long ns[64];
     DPGO_CUDA(cudaStreamSynchronize(p->stream));
     DPGO_CUDA(cudaMemcpy(ns, p->d_phase_ns, sizeof(ns), cudaMemcpyDeviceToHost));
     if (ms_by_kind)
-      for (int i = 0; i < 8; ++i) ms_by_kind[i] = 1e-6 * (double)ns[i];
+      for (int i = 0; i < nout; ++i) ms_by_kind[i] = 1e-6 * (double)ns[i];
     DPGO_CUDA(cudaMemset(p->d_phase_ns, 0, sizeof(ns)));
     if (!enable) { cudaFree(p->d_phase_ns); p->d_phase_ns = nullptr; }
   } else if (ms_by_kind) {
-    for (int i = 0; i < 8; ++i) ms_by_kind[i] = 0.0;
+    for (int i = 0; i < nout; ++i) ms_by_kind[i] = 0.0;
   }
   return DPGO_OK;
 }
+
+int dpgo_debug_phase_times(dpgo_problem_t *p, int enable, double *ms_by_kind) { return phase_times_impl(p, enable, ms_by_kind, 8); }
+int dpgo_debug_phase_times32(dpgo_problem_t *p, int enable, double *ms_by_kind) { return phase_times_impl(p, enable, ms_by_kind, 32); }
+int dpgo_debug_phase_times64(dpgo_problem_t *p, int enable, double *ms_by_kind) { return phase_times_impl(p, enable, ms_by_kind, 64); }
 
 int dpgo_spmv_device(dpgo_problem_t *p, const double *X_dev, double *out_dev, int add_G) {
   DPGO_CHECK_HANDLE(p);
@@ -1077,6 +1092,25 @@ int dpgo_nd_debug_emulate(int n, int d, int r, int64_t nb, const int32_t *brow, 
       return fail(DPGO_ERR_UNSUPPORTED, "plan exceeds the shared-memory capacities");
     nd::emulate_apply(H, plan, blob, r, V_host, Z_host);
     if (info16) nd_fill_info(H, plan, info16);
+    if (const char *dump = std::getenv("DPGO_ND_DUMP_PLAN")) {            // per (phase, CTA) work statistics, CSV
+      if (FILE *fp = std::fopen(dump, "w")) {
+        std::fprintf(fp, "phase,dir,stage,cta,steps,gather_tiles,jobs,job_cols,max_warp_cols,epis\n");
+        for (size_t ph = 0; ph < plan.phases.size(); ++ph)
+          for (int c = 0; c < plan.grid; ++c) {
+            const nd::CtaPhase &cp = plan.cta_phase[(size_t)plan.phases[ph].cta0 + c];
+            long gt = 0, nj = 0, jc = 0, ne = 0, mw = 0;
+            for (int si = cp.s0; si < cp.s1; ++si) {
+              const nd::Step &st = plan.steps[(size_t)si];
+              gt += st.g1 - st.g0; nj += st.j1 - st.j0; ne += st.e1 - st.e0;
+              std::vector<long> w((size_t)opt.warps, 0);
+              for (int j = st.j0; j < st.j1; ++j) { jc += plan.jobs[(size_t)j].ncols; w[(size_t)((j - st.j0) % opt.warps)] += plan.jobs[(size_t)j].ncols + 40; }
+              mw += *std::max_element(w.begin(), w.end());
+            }
+            std::fprintf(fp, "%zu,%d,%d,%d,%d,%ld,%ld,%ld,%ld,%ld\n", ph, plan.phases[ph].dir, plan.phases[ph].stage, c, cp.s1 - cp.s0, gt, nj, jc, mw, ne);
+          }
+        std::fclose(fp);
+      }
+    }
   } catch (const std::exception &e) {
     return fail(DPGO_ERR_UNSUPPORTED, std::string("sparse exact preconditioner: ") + e.what());
   }

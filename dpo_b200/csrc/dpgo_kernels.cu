@@ -12,6 +12,7 @@
 #include "dpgo_device.cuh"
 #include "dpgo_kernels.cuh"
 #include <cooperative_groups.h>
+#include <algorithm>
 
 namespace dpgo {
 
@@ -41,7 +42,7 @@ __device__ __forceinline__ void phase_end(const KParams &kp, BlockCtx &bc, doubl
     for (int w = 0; w < nwarps; ++w) s += bc.sm_warp[w * NRED + threadIdx.x];
     slot[(size_t)blockIdx.x * NRED + threadIdx.x] = s;
   }
-  grid_barrier(kp.bar_counter, bc.epoch);
+  grid_barrier(kp.bar_counter, bc.epoch, kp.strict_acquire);
   if (NUSED > 0) {
     if (warp == 0) {
       double s[NUSED > 0 ? NUSED : 1];
@@ -700,111 +701,188 @@ __device__ __forceinline__ int4 ld_int4(const void *p) { return __ldg(reinterpre
 
 template <int R, int DH>
 __device__ void phase_nd(const KParams &kp, int ph, const double *V, int cb, double *Zout, double *ys, double *slots,
-                         double (&acc)[NRED]) {
+                         int4 *grec, double (&acc)[NRED]) {
   constexpr int TS = R * DH;
   constexpr int SG = SubGroup<R>::SG;
   constexpr int SGW = 32 / SG;
   constexpr int SLOT = nd::PANEL_ROWS * R;
+  constexpr int NC = nd::INLINE_CONTRIB;
   const KNd &N = kp.nd;
-  const int4 P = ld_int4(N.phases + ph);                  // dir, stage, step_ptr0, pad
-  const int dir = P.x;
-  const int s0 = ld_const(N.cta_step + P.z + blockIdx.x), s1 = ld_const(N.cta_step + P.z + blockIdx.x + 1);
+  const int dir = N.dir[ph];
+  const int4 ca = ld_int4(N.cta_phase + N.cta0[ph] + blockIdx.x),
+             cbq = ld_int4(reinterpret_cast<const int4 *>(N.cta_phase + N.cta0[ph] + blockIdx.x) + 1);
+  const int s0 = ca.x, s1 = ca.y;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
   const int sgw = lane / SG, l = lane & (SG - 1), a = l >> 2, c = l & 3;
   const bool valid = (a < R) && (c < DH);
   const int e = c * R + a;
-  const int nsub = nwarps * SGW, sub = warp * SGW + sgw;
+  const int nsub = nwarps * SGW;
   const double *X = kp.v[V_X0 + cb];
   const double *src = (dir == 0) ? V : N.TX;
+  const bool ticking = (kp.phase_ns != nullptr) && blockIdx.x == 0 && threadIdx.x == 0;
   for (int si = s0; si < s1; ++si) {
-    const int4 sa = ld_int4(N.steps + si), sb = ld_int4(reinterpret_cast<const int4 *>(N.steps + si) + 1);
-    const int g0 = sa.x, g1 = sa.y, j0 = sa.z, j1 = sa.w, e0 = sb.x, e1 = sb.y;
-    // ---- gathers ----
-    for (int gi = g0 + sub; gi < g1; gi += nsub) {
-      const int4 g = ld_int4(N.gathers + gi);             // ytile, src, c0, c1
-      if (valid) {
-        double v = __ldcg(src + (size_t)g.y * TS + e);
-        for (int k = g.z; k < g.w; ++k) v -= __ldcg(N.C + (size_t)ld_const(N.csrc + k) * TS + e);
-        ys[(size_t)g.x * TS + e] = v;
+    int g0 = ca.z, g1 = ca.w, j0 = cbq.x, j1 = cbq.y, e0 = cbq.z, e1 = cbq.w;      // the first step sits in the CTA record
+    if (si != s0) {
+      const int4 sa = ld_int4(N.steps + si), sb = ld_int4(reinterpret_cast<const int4 *>(N.steps + si) + 1);
+      g0 = sa.x; g1 = sa.y; j0 = sa.z; j1 = sa.w; e0 = sb.x; e1 = sb.y;
+    }
+    unsigned long long tg0 = 0, tg1 = 0, tg2 = 0;
+    if (ticking) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tg0));
+    // ---- gathers: the step's records are staged in shared memory with one coalesced sweep (one L2 round trip), then
+    //      the loop is flat over (tile, element) with 4 independent elements per thread and round ----
+    {
+      const int ng = g1 - g0;
+      const int4 *gsrc = reinterpret_cast<const int4 *>(N.gathers + g0);
+      for (int q = threadIdx.x; q < 2 * ng; q += blockDim.x) grec[q] = __ldg(gsrc + q);
+      __syncthreads();
+      constexpr int GU = 4;
+      const int total = ng * TS, nthr = blockDim.x;
+      for (int base = threadIdx.x; base < total; base += GU * nthr) {
+        int t[GU], el[GU];
+        bool ok[GU];
+        double v[GU], cv[GU][NC];
+#pragma unroll
+        for (int u = 0; u < GU; ++u) {
+          const int idx = base + u * nthr;
+          ok[u] = idx < total;
+          t[u] = ok[u] ? idx / TS : 0;
+          el[u] = idx - t[u] * TS;
+          const int4 ra = grec[2 * t[u]], rb = grec[2 * t[u] + 1];             // (ytile, src, nc, cext), first contribution tiles
+          v[u] = ok[u] ? __ldcg(src + (size_t)ra.y * TS + el[u]) : 0.0;
+          const int ci[NC] = {rb.x, rb.y, rb.z, rb.w};
+#pragma unroll
+          for (int q = 0; q < NC; ++q) cv[u][q] = (ok[u] && q < ra.z) ? __ldcg(N.C + (size_t)ci[q] * TS + el[u]) : 0.0;
+        }
+#pragma unroll
+        for (int u = 0; u < GU; ++u) {
+          const int4 ra = grec[2 * t[u]];
+#pragma unroll
+          for (int q = 0; q < NC; ++q) v[u] -= cv[u][q];
+          for (int k = NC; k < ra.z && ok[u]; ++k)
+            v[u] -= __ldcg(N.C + (size_t)ld_const(N.csrc + ra.w + k - NC) * TS + el[u]);
+          if (ok[u]) ys[(size_t)ra.x * TS + el[u]] = v[u];
+        }
       }
     }
     __syncthreads();
-    // ---- jobs ----
+    if (ticking) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tg1));
+    // ---- jobs: DMMA m8n8k4 -- A = 8 panel rows x 4 columns (one coalesced 256-byte warp load), B = 4 columns x r
+    //      right-hand sides from shared memory, D = 8 x 8 accumulators (r columns used): 1 LDG + 1 LDS + 1 DMMA per
+    //      4 columns instead of 1 LDG + r LDS + r DFMA per lane, and no shuffle reduction.  Two accumulator chains;
+    //      the next job's record is fetched ahead.
     {
-      const int row = lane & 7, cp = lane >> 3;
-      for (int ji = j0 + warp; ji < j1; ji += nwarps) {
-        const int4 ja = ld_int4(N.jobs + ji), jb = ld_int4(reinterpret_cast<const int4 *>(N.jobs + ji) + 1);
+      const int r8 = lane >> 2, k4 = lane & 3;
+      const bool bval_lane = (r8 < R);
+      int ji = j0 + warp;
+      int4 ja = make_int4(0, 0, 0, 0), jb = make_int4(0, 0, 0, 0);
+      if (ji < j1) { ja = ld_int4(N.jobs + ji); jb = ld_int4(reinterpret_cast<const int4 *>(N.jobs + ji) + 1); }
+      while (ji < j1) {
+        const int jn = ji + nwarps;
+        int4 na = make_int4(0, 0, 0, 0), nb = make_int4(0, 0, 0, 0);
+        if (jn < j1) { na = ld_int4(N.jobs + jn); nb = ld_int4(reinterpret_cast<const int4 *>(N.jobs + jn) + 1); }
         const long long mat = ((long long)(unsigned)ja.x) | ((long long)ja.y << 32);
         const int ncols = ja.z, ycol = ja.w, slot = jb.x, accum = jb.y;
-        const double *mp = N.blob + mat + row;
-        const double *yp = ys + (size_t)ycol * R;
-        double av[R];
+        const double *mp = N.blob + mat + (size_t)k4 * nd::PANEL_ROWS + r8;      // A[r8][k4] of the first column group
+        const double *yp = ys + (size_t)(ycol + k4) * R + (bval_lane ? r8 : 0);    // B[k4][r8]
+        double d0 = 0.0, d1 = 0.0, f0 = 0.0, f1 = 0.0;
+        for (int j = 0; j < ncols; j += 32) {                                        // 8 column groups (32 columns) per round
+          double am[8], bm[8];
+          if (j + 32 <= ncols) {
 #pragma unroll
-        for (int q = 0; q < R; ++q) av[q] = 0.0;
-        int j = cp;
-        for (; j + 28 < ncols; j += 32) {
-          double m[8];
+            for (int u = 0; u < 8; ++u) am[u] = ld_stream(mp + (size_t)(j + 4 * u) * nd::PANEL_ROWS);
 #pragma unroll
-          for (int u = 0; u < 8; ++u) m[u] = ld_stream(mp + (size_t)(j + 4 * u) * nd::PANEL_ROWS);
+            for (int u = 0; u < 8; ++u) bm[u] = bval_lane ? yp[(size_t)(j + 4 * u) * R] : 0.0;
+          } else {                                                                   // last, ragged round: same 8 independent loads, predicated
 #pragma unroll
-          for (int u = 0; u < 8; ++u) {
-            const double *y = yp + (size_t)(j + 4 * u) * R;
+            for (int u = 0; u < 8; ++u) am[u] = (j + 4 * u + k4 < ncols) ? ld_stream(mp + (size_t)(j + 4 * u) * nd::PANEL_ROWS) : 0.0;
 #pragma unroll
-            for (int q = 0; q < R; ++q) av[q] = fma(m[u], y[q], av[q]);
+            for (int u = 0; u < 8; ++u) bm[u] = (bval_lane && j + 4 * u + k4 < ncols) ? yp[(size_t)(j + 4 * u) * R] : 0.0;
+          }
+#pragma unroll
+          for (int u = 0; u < 8; u += 2) {
+            dmma884(d0, d1, am[u], bm[u]);
+            dmma884(f0, f1, am[u + 1], bm[u + 1]);
           }
         }
-        for (; j < ncols; j += 4) {
-          const double m = ld_stream(mp + (size_t)j * nd::PANEL_ROWS);
-          const double *y = yp + (size_t)j * R;
-#pragma unroll
-          for (int q = 0; q < R; ++q) av[q] = fma(m, y[q], av[q]);
+        d0 += f0;
+        d1 += f1;
+        {
+          double *sl = slots + (size_t)slot * SLOT + r8 * R + 2 * k4;              // D[r8][2 k4], D[r8][2 k4 + 1]
+          if (2 * k4 < R) sl[0] = accum ? sl[0] + d0 : d0;
+          if (2 * k4 + 1 < R) sl[1] = accum ? sl[1] + d1 : d1;
         }
-#pragma unroll
-        for (int q = 0; q < R; ++q) {
-          av[q] += shfl_xor(av[q], 8);
-          av[q] += shfl_xor(av[q], 16);
-        }
-        if (cp == 0) {
-          double *sl = slots + (size_t)slot * SLOT + row * R;
-#pragma unroll
-          for (int q = 0; q < R; ++q) sl[q] = accum ? sl[q] + av[q] : av[q];
-        }
+        ji = jn; ja = na; jb = nb;
       }
     }
     __syncthreads();
-    // ---- epilogues (warp-uniform trip count: the projection uses full-warp shuffles) ----
-    for (int eb = e0 + warp * SGW; eb < e1; eb += nsub) {
-      const int ei = eb + sgw;
-      const bool act = (ei < e1);
-      int4 ea = make_int4(-1, 0, 0, 0), ec = make_int4(0, 0, 0, 0);
-      if (act) { ea = ld_int4(N.epis + ei); ec = ld_int4(reinterpret_cast<const int4 *>(N.epis + ei) + 1); }
-      const int kind = ea.x, slot0 = ea.y, nslots = ea.z, half = ea.w, out = ec.x, aux = ec.y, c0 = ec.z, c1 = ec.w;
-      const bool ld = act && valid;
-      double sum = 0.0;
-      if (ld) {
-        const double *sl = slots + (size_t)slot0 * SLOT + (half * DH + c) * R + a;
-        for (int k = 0; k < nslots; ++k) sum += sl[(size_t)k * SLOT];
+    if (ticking) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tg2));
+    // ---- epilogues (warp-uniform trip count: the projection uses full-warp shuffles); global loads first, the next
+    //      item's record is fetched ahead ----
+    {
+      int eb = e0 + warp * SGW;
+      int4 ea = make_int4(-1, 0, 0, 0), ec = make_int4(0, 0, 0, 0), ed = make_int4(0, 0, 0, 0);
+      if (eb + sgw < e1) {
+        const int4 *rp = reinterpret_cast<const int4 *>(N.epis + eb + sgw);
+        ea = __ldg(rp); ec = __ldg(rp + 1); ed = __ldg(rp + 2);
       }
-      const bool sol = (kind == nd::EPI_ROOT) || (kind == nd::EPI_B_OWN);
-      double x = 0.0, xq = 0.0;
-      if (ld) {
-        if (kind == nd::EPI_F_OWN) {
-          N.TX[(size_t)out * TS + e] = sum;
-        } else if (kind == nd::EPI_F_BND) {
-          for (int k = c0; k < c1; ++k) sum += __ldcg(N.C + (size_t)ld_const(N.csrc + k) * TS + e);
-          N.C[(size_t)out * TS + e] = sum;
-        } else if (sol) {
-          x = (kind == nd::EPI_ROOT) ? sum : __ldcg(N.TX + (size_t)out * TS + e) - sum;
-          N.TX[(size_t)out * TS + e] = x;
-          xq = __ldcg(X + (size_t)aux * TS + e);
+      while (eb < e1) {
+        const int en = eb + nsub;
+        int4 fa = make_int4(-1, 0, 0, 0), fc = make_int4(0, 0, 0, 0), fd = make_int4(0, 0, 0, 0);
+        if (en + sgw < e1) {
+          const int4 *rp = reinterpret_cast<const int4 *>(N.epis + en + sgw);
+          fa = __ldg(rp); fc = __ldg(rp + 1); fd = __ldg(rp + 2);
         }
+        const bool act = (eb + sgw < e1);
+        const int kind = ea.x, slot0 = ea.y, nslots = ea.z, half = ea.w, out = ec.x, aux = ec.y, nc = ec.z, cext = ec.w;
+        const bool ld = act && valid;
+        const bool sol = (kind == nd::EPI_ROOT) || (kind == nd::EPI_B_OWN);
+        // independent global loads: t (backward), X and V tiles (solution poses), contributions (boundary rows)
+        double tval = 0.0, xq = 0.0, vv = 0.0, cv[NC] = {0.0, 0.0, 0.0, 0.0};
+        if (ld) {
+          if (kind == nd::EPI_B_OWN) tval = __ldcg(N.TX + (size_t)out * TS + e);
+          if (sol) { xq = __ldcg(X + (size_t)aux * TS + e); vv = __ldcg(V + (size_t)aux * TS + e); }
+          if (kind == nd::EPI_F_BND) {
+            const int ci[NC] = {ed.x, ed.y, ed.z, ed.w};
+#pragma unroll
+            for (int q = 0; q < NC; ++q) cv[q] = (q < nc) ? __ldcg(N.C + (size_t)ci[q] * TS + e) : 0.0;
+          }
+        }
+        double sum = 0.0;
+        if (ld) {
+          const double *sl = slots + (size_t)slot0 * SLOT + (half * DH + c) * R + a;
+          for (int k = 0; k < nslots; ++k) sum += sl[(size_t)k * SLOT];
+        }
+        double x = 0.0;
+        if (ld) {
+          if (kind == nd::EPI_F_OWN) {
+            N.TX[(size_t)out * TS + e] = sum;
+          } else if (kind == nd::EPI_F_BND) {
+#pragma unroll
+            for (int q = 0; q < NC; ++q) sum += cv[q];
+            for (int k = NC; k < nc; ++k) sum += __ldcg(N.C + (size_t)ld_const(N.csrc + cext + k - NC) * TS + e);
+            N.C[(size_t)out * TS + e] = sum;
+          } else if (sol) {
+            x = (kind == nd::EPI_ROOT) ? sum : tval - sum;
+            N.TX[(size_t)out * TS + e] = x;
+          }
+        }
+        if (__any_sync(FULL, sol)) {                      // forward sweeps below the root have nothing to project
+          double ya[3], sym[3];
+          const double z = tangent_project_elem<R, DH>(sol ? xq : 0.0, x, a, c, ya, sym);
+          if (ld && sol) {
+            Zout[(size_t)aux * TS + e] = z;
+            acc[0] = fma(z, vv, acc[0]);
+          }
+        }
+        eb = en; ea = fa; ec = fc; ed = fd;
       }
-      double ya[3], sym[3];
-      const double z = tangent_project_elem<R, DH>(xq, x, a, c, ya, sym);
-      if (ld && sol) {
-        Zout[(size_t)aux * TS + e] = z;
-        acc[0] = fma(z, __ldcg(V + (size_t)aux * TS + e), acc[0]);
-      }
+    }
+    if (ticking) {
+      unsigned long long tg3;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tg3));
+      kp.phase_ns[24] += tg1 - tg0; kp.phase_ns[25] += tg2 - tg1; kp.phase_ns[26] += tg3 - tg2;
+      unsigned long long *pp = kp.phase_ns + 32 + 3 * min(ph, 9);
+      pp[0] += tg1 - tg0; pp[1] += tg2 - tg1; pp[2] += tg3 - tg2;
     }
     // the next step's gathers / jobs rewrite ys / slots only after every warp is past its epilogues
     if (si + 1 < s1) __syncthreads();
@@ -900,7 +978,7 @@ template <int R, int DH> __global__ void __launch_bounds__(OPT_THREADS, 1) k_opt
   ring.count = 0;
   int *sMeta = reinterpret_cast<int *>(ring.empty + DENSE_NST);         // symmetric variant: (segment, first row) per window slot
   // bulk-TMA streaming needs 16-byte aligned rows (N even) and only pays off for a real stream
-  const bool dense_tma = (kp.pinv != nullptr) && ((kp.N & 1) == 0) && (kp.N >= 2048);
+  const bool dense_tma = (kp.prm.precond == DPGO_PRECOND_DENSE_EXACT) && (kp.pinv != nullptr) && ((kp.N & 1) == 0) && (kp.N >= 2048);
   const bool dense_sym = dense_tma && (kp.sym_ok != 0);
   if (dense_tma) {
     if (dense_sym) {       // stale shared memory must be finite: tiles past N are multiplied by zero operands
@@ -936,17 +1014,18 @@ template <int R, int DH> __global__ void __launch_bounds__(OPT_THREADS, 1) k_opt
   double acc[NRED];
   // sparse exact preconditioner: shared memory = gathered input tiles + partial-sum slots (aliases the dense ring)
   double *nd_ys = sV;
-  double *nd_slots = sV + (size_t)ND_YCAP_TILES * R * DH;
+  double *nd_slots = sV + (size_t)kp.nd.max_ytiles * R * DH;
+  int4 *nd_grec = reinterpret_cast<int4 *>((reinterpret_cast<uintptr_t>(nd_slots + (size_t)kp.nd.max_slots * nd::PANEL_ROWS * R) + 15) & ~(uintptr_t)15);
   // Z = P_X( (Q + 0.1 I)^-1 V ), returns <Z, V> in acc[0]; every phase ends with a grid barrier
   auto apply_exact = [&](const double *Vv, int cbx, double *Zout) {
     if (precond == DPGO_PRECOND_SPARSE_EXACT) {
       zero(acc);
       for (int ph = 0; ph < kp.nd.nphases; ++ph) {
-        phase_nd<R, DH>(kp, ph, Vv, cbx, Zout, nd_ys, nd_slots, acc);
-        if (ph + 1 < kp.nd.nphases) phase_end<0>(kp, bc, acc);
+        phase_nd<R, DH>(kp, ph, Vv, cbx, Zout, nd_ys, nd_slots, nd_grec, acc);
+        if (ph + 1 < kp.nd.nphases) { phase_end<0>(kp, bc, acc); tick(8 + min(ph, 15)); }
       }
       phase_end<1>(kp, bc, acc);
-      tick(1);
+      tick(8 + min(kp.nd.nphases - 1, 15));
     } else {
       if (dense_sym) phase_dense_sym<R>(kp, Vv, ring, sV, sMeta);
       else if (dense_tma) phase_dense_tma<R>(kp, Vv, sV, ring);
@@ -1322,15 +1401,44 @@ __global__ void k_build_G(int nposes, const int *__restrict__ pose_ids, const in
 // ---------------------------------------------------------------------------------------------
 // launchers
 // ---------------------------------------------------------------------------------------------
-template <int R, int DH> static cudaError_t launch_optimize_t(const KParams &kp, cudaStream_t stream) {
-  const size_t smem = ((OPT_THREADS / 32) * NRED + NRED + (size_t)DENSE_PER_MAX * R + (size_t)DENSE_RING_DOUBLES + 2 * DENSE_NST + (size_t)SYM_META_DOUBLES) * sizeof(double);
+// Dynamic shared memory of one launch: the reduction scratch, plus what the launch's preconditioner stages (the dense
+// ring or the sparse plan's tiles and slots).  Asking for no more than needed leaves the rest of the SM's 228 KB to L1,
+// which now keeps the constant data (block-CSR, plan records) across phases.
+template <int R, int DH> static size_t optimize_smem_doubles(const KParams &kp, bool max_only) {
+  const size_t base = (OPT_THREADS / 32) * NRED + NRED;
+  const size_t dense = (size_t)DENSE_PER_MAX * R + (size_t)DENSE_RING_DOUBLES + 2 * DENSE_NST + (size_t)SYM_META_DOUBLES;
+  if (max_only || kp.prm.precond == DPGO_PRECOND_DENSE_EXACT) return base + dense;
+  if (kp.prm.precond == DPGO_PRECOND_SPARSE_EXACT)
+    return base + (size_t)kp.nd.max_ytiles * R * DH + (size_t)(kp.nd.max_slots + 1) * nd::PANEL_ROWS * R + 4 * (size_t)kp.nd.max_gathers + 8;
+  return base + 8;
+}
+
+template <int R, int DH> static cudaError_t launch_optimize_t(const KParams &kp_in, cudaStream_t stream) {
+  KParams kp = kp_in;
+  const size_t smem_max = optimize_smem_doubles<R, DH>(kp, true) * sizeof(double);
+  static_assert((size_t)ND_YCAP_TILES * R * DH + (size_t)(ND_SLOT_CAP + 1) * nd::PANEL_ROWS * R + 4 * (size_t)ND_YCAP_TILES + 8 <=
+                    (size_t)DENSE_PER_MAX * R + (size_t)DENSE_RING_DOUBLES + 2 * DENSE_NST + (size_t)SYM_META_DOUBLES,
+                "the sparse plan's capacities must fit the kernel's maximum shared memory");
+  kp.smem_doubles = (int)optimize_smem_doubles<R, DH>(kp, false);
+  const size_t smem = (size_t)kp.smem_doubles * sizeof(double);
   static bool attr_set[64] = {};
   int dev = 0;
   cudaGetDevice(&dev);
   if (dev < 0 || dev >= 64 || !attr_set[dev]) {
-    cudaError_t e = cudaFuncSetAttribute(k_optimize<R, DH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(k_optimize<R, DH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max);
     if (e != cudaSuccess) return e;
     if (dev >= 0 && dev < 64) attr_set[dev] = true;
+  }
+  {
+    // shared-memory carve-out hint: what this launch needs (+ the 1 KB the system reserves), so that L1 gets the rest
+    static int last_pct[64];
+    static bool init = false;
+    if (!init) { for (int i = 0; i < 64; ++i) last_pct[i] = -1; init = true; }
+    const int pct = std::min(100, (int)((smem + 2048) * 100 / (228 * 1024)) + 1);
+    if (dev >= 0 && dev < 64 && last_pct[dev] != pct) {
+      cudaFuncSetAttribute(k_optimize<R, DH>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+      last_pct[dev] = pct;
+    }
   }
   void *args[] = {(void *)&kp};
   return cudaLaunchCooperativeKernel((void *)k_optimize<R, DH>, dim3(kp.grid), dim3(OPT_THREADS), args, smem, stream);

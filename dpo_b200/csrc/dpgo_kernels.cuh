@@ -41,8 +41,11 @@ constexpr int DENSE_PER_MAX = 512;  // max rows of the dense inverse one CTA own
 // sparse exact preconditioner (nd_precond.h): the static plan and the panel blob in HBM / L2
 struct KNd {
   int nphases;
-  const nd::Phase *phases;
-  const int *cta_step;
+  int max_ytiles, max_slots;       // shared-memory tiles / partial-sum slots the plan needs per step
+  int max_gathers;                 // gather records staged per step (<= max_ytiles)
+  int dir[nd::MAX_PHASES];         // per phase: 0 forward (input = residual), 1 backward (input = ancestors' solution)
+  int cta0[nd::MAX_PHASES];        // per phase: first (phase, CTA) record
+  const nd::CtaPhase *cta_phase;
   const nd::Step *steps;
   const nd::Gather *gathers;
   const nd::Job *jobs;
@@ -83,6 +86,8 @@ struct KParams {
   dpgo_opt_params_t prm;
   dpgo_opt_result_t *result;   // device copy of the result record
   KNd nd;                // sparse exact preconditioner (nd.nphases == 0: not prepared)
+  int strict_acquire;    // 1: the grid barrier polls with ld.acquire (L1 invalidated every phase); 0: relaxed poll (default)
+  int smem_doubles;      // dynamic shared memory of this launch, in doubles
   unsigned long long *phase_ns; // diagnostic (nullable): per phase kind, ns seen by CTA 0 (dpgo_debug_phase_times)
 };
 

@@ -608,6 +608,9 @@ void build_numeric(const BsrView &Q, const Options &opt, Hierarchy &H, std::vect
 namespace {
 
 struct Run { int node; int p0, p1; double cost; };
+// cost of one panel besides its streamed columns, in column units: two epilogue items (record, slot sums, projection,
+// stores: ~1000 cycles each on one of 16 warps) against ~2-3 cycles per streamed 64-byte column
+constexpr double PANEL_FIXED_COST = 48.0;
 
 struct PhaseBuilder {
   const Hierarchy &H;
@@ -641,10 +644,12 @@ struct PhaseBuilder {
     return cl;
   }
 
-  int push_csrc(const std::vector<int> &v, int &c0) {
-    c0 = (int)P.csrc.size();
-    P.csrc.insert(P.csrc.end(), v.begin(), v.end());
-    return (int)P.csrc.size();
+  // contribution list -> (count, inline ids, pointer to the remaining ids in csrc)
+  void set_contrib(const std::vector<int> &v, int &nc, int &cext, int *ci) {
+    nc = (int)v.size();
+    cext = (int)P.csrc.size();
+    for (int q = 0; q < INLINE_CONTRIB; ++q) ci[q] = (q < nc) ? v[(size_t)q] : 0;
+    for (int q = INLINE_CONTRIB; q < nc; ++q) P.csrc.push_back(v[(size_t)q]);
   }
 
   void build() {
@@ -658,14 +663,14 @@ struct PhaseBuilder {
     double total = 0.0;
     for (int m : nodes) {
       const MacroNode &mn = H.nodes[(size_t)m];
-      total += (double)ceil_div(rows_of(mn), 2) * (cols_of(mn) * dh + 16.0);
+      total += (double)ceil_div(rows_of(mn), 2) * (cols_of(mn) * dh + PANEL_FIXED_COST);
     }
     const double target = std::max(total / G, 1.0);
     std::vector<Run> runs;
     for (int m : nodes) {
       const MacroNode &mn = H.nodes[(size_t)m];
       const int np = ceil_div(rows_of(mn), 2);
-      const double pc = cols_of(mn) * dh + 16.0;            // cost of one panel
+      const double pc = cols_of(mn) * dh + PANEL_FIXED_COST;   // cost of one panel: streamed columns + its two epilogues
       const double cost = np * pc;
       int k = (int)std::floor(cost / target + 0.5);
       k = std::max(1, std::min(k, np));
@@ -687,15 +692,19 @@ struct PhaseBuilder {
       load[(size_t)bestc] += runs[(size_t)ri].cost;
       mine[(size_t)bestc].push_back(ri);
     }
-    const int ph = (int)P.phases.size();
-    P.phases.push_back({dir, stage, (int)P.cta_step.size(), 0});
+    P.phases.push_back({dir, stage, (int)P.cta_phase.size(), 0});
     for (int c = 0; c < G; ++c) {
-      P.cta_step.push_back((int)P.steps.size());
+      const int s0 = (int)P.steps.size();
       std::sort(mine[(size_t)c].begin(), mine[(size_t)c].end());
       emit_cta(mine[(size_t)c], runs);
+      const int s1 = (int)P.steps.size();
+      CtaPhase cp = {s0, s1, 0, 0, 0, 0, 0, 0};
+      if (s1 > s0) {
+        const Step &st = P.steps[(size_t)s0];
+        cp.g0 = st.g0; cp.g1 = st.g1; cp.j0 = st.j0; cp.j1 = st.j1; cp.e0 = st.e0; cp.e1 = st.e1;
+      }
+      P.cta_phase.push_back(cp);
     }
-    P.cta_step.push_back((int)P.steps.size());
-    (void)ph;
   }
 
   // one CTA: group its runs into steps
@@ -774,7 +783,7 @@ struct PhaseBuilder {
         int yb0 = 0;
         for (auto &yb : ybase) if (yb.first == work[q].node) yb0 = yb.second;
         const int ct = cols_of(H.nodes[(size_t)work[q].node]);
-        const int pc = std::max(1, std::min(pieces, std::max(1, ct * dh / 16)));
+        const int pc = std::max(1, std::min(pieces, std::max(1, ct * dh / 32)));
         slot0s.push_back(slot);
         emit_jobs(work[q], 0, ct, yb0, slot, pc, false);
         slot += (work[q].p1 - work[q].p0) * pc;
@@ -783,7 +792,7 @@ struct PhaseBuilder {
       st.e0 = (int)P.epis.size();
       for (size_t q = i; q < j; ++q) {
         const int ct = cols_of(H.nodes[(size_t)work[q].node]);
-        const int pc = std::max(1, std::min(pieces, std::max(1, ct * dh / 16)));
+        const int pc = std::max(1, std::min(pieces, std::max(1, ct * dh / 32)));
         emit_epis(work[q], slot0s[q - i], pc);
       }
       st.e1 = (int)P.epis.size();
@@ -794,10 +803,12 @@ struct PhaseBuilder {
     }
   }
 
+  // column pieces per panel: about one job per warp (a job has a fixed cost of a few hundred issue slots), none
+  // shorter than 32 columns (one full round of the DMMA loop)
   int pieces_for(int panels, int ncols) const {
-    const int want = 2 * opt.warps;
-    int pieces = std::max(1, ceil_div(want, std::max(panels, 1)));
-    pieces = std::min(pieces, std::max(1, ncols / 16));
+    const int want = opt.warps;
+    int pieces = std::max(1, want / std::max(panels, 1));
+    pieces = std::min(pieces, std::max(1, ncols / 32));
     pieces = std::min(pieces, std::max(1, opt.slot_cap / std::max(panels, 1)));
     return pieces;
   }
@@ -806,15 +817,13 @@ struct PhaseBuilder {
   void emit_gathers(int m, int t0, int t1, int ybase) {
     const MacroNode &mn = H.nodes[(size_t)m];
     for (int t = t0; t < t1; ++t) {
-      Gather g;
+      Gather g = {};
       g.ytile = ybase + (t - t0);
       if (dir == 0) {
         g.src = mn.own[(size_t)t];                                    // pose id: source = V
-        const auto &cl = contributions(m)[(size_t)t];
-        g.c1 = push_csrc(cl, g.c0);
+        set_contrib(contributions(m)[(size_t)t], g.nc, g.cext, g.ci);
       } else {
         g.src = H.iperm[(size_t)mn.bnd[(size_t)t]];                   // permuted tile: source = TX (solution of the ancestors)
-        g.c0 = g.c1 = 0;
       }
       P.gathers.push_back(g);
     }
@@ -856,7 +865,6 @@ struct PhaseBuilder {
         e.slot0 = slot_base + (p - r.p0) * pieces;
         e.nslots = has_cols ? pieces : 0;
         e.half = half;
-        e.c0 = e.c1 = 0;
         if (dir == 0) {
           if (fr < no) {
             e.kind = root ? EPI_ROOT : EPI_F_OWN;
@@ -866,8 +874,7 @@ struct PhaseBuilder {
             e.kind = EPI_F_BND;
             e.out = mn.cbuf0 + (fr - no);
             e.aux = -1;
-            const auto &cl = contributions(r.node)[(size_t)fr];
-            e.c1 = push_csrc(cl, e.c0);
+            set_contrib(contributions(r.node)[(size_t)fr], e.nc, e.cext, e.ci);
           }
         } else {
           e.kind = EPI_B_OWN;
@@ -908,7 +915,13 @@ void emulate_apply(const Hierarchy &H, const Plan &P, const std::vector<double> 
   for (size_t ph = 0; ph < P.phases.size(); ++ph) {
     const Phase &phs = P.phases[ph];
     for (int c = 0; c < P.grid; ++c) {
-      const int s0 = P.cta_step[(size_t)phs.step_ptr0 + c], s1 = P.cta_step[(size_t)phs.step_ptr0 + c + 1];
+      const CtaPhase &cph = P.cta_phase[(size_t)phs.cta0 + c];
+      const int s0 = cph.s0, s1 = cph.s1;
+      if (s1 > s0) {                                                    // the inline copy of the first step must agree
+        const Step &f = P.steps[(size_t)s0];
+        if (f.g0 != cph.g0 || f.g1 != cph.g1 || f.j0 != cph.j0 || f.j1 != cph.j1 || f.e0 != cph.e0 || f.e1 != cph.e1)
+          throw std::runtime_error("nd: inline first step disagrees with the step table");
+      }
       std::fill(slots.begin(), slots.end(), std::nan(""));            // a slot must be written before it is read
       for (int si = s0; si < s1; ++si) {
         const Step &st = P.steps[(size_t)si];
@@ -917,7 +930,10 @@ void emulate_apply(const Hierarchy &H, const Plan &P, const std::vector<double> 
           const Gather &g = P.gathers[(size_t)gi];
           for (int e = 0; e < ts; ++e) {
             double v = (phs.dir == 0) ? V[(size_t)g.src * ts + e] : TX[(size_t)g.src * ts + e];
-            for (int k = g.c0; k < g.c1; ++k) v -= C[(size_t)P.csrc[(size_t)k] * ts + e];
+            for (int k = 0; k < g.nc; ++k) {
+              const int ct = (k < INLINE_CONTRIB) ? g.ci[k] : P.csrc[(size_t)(g.cext + k - INLINE_CONTRIB)];
+              v -= C[(size_t)ct * ts + e];
+            }
             ys[(size_t)g.ytile * ts + e] = v;
           }
         }
@@ -942,7 +958,10 @@ void emulate_apply(const Hierarchy &H, const Plan &P, const std::vector<double> 
               if (ep.kind == EPI_F_OWN) {
                 TX[(size_t)ep.out * ts + e] = sum;
               } else if (ep.kind == EPI_F_BND) {
-                for (int k = ep.c0; k < ep.c1; ++k) sum += C[(size_t)P.csrc[(size_t)k] * ts + e];
+                for (int k = 0; k < ep.nc; ++k) {
+                  const int ct = (k < INLINE_CONTRIB) ? ep.ci[k] : P.csrc[(size_t)(ep.cext + k - INLINE_CONTRIB)];
+                  sum += C[(size_t)ct * ts + e];
+                }
                 C[(size_t)ep.out * ts + e] = sum;
               } else if (ep.kind == EPI_ROOT) {
                 TX[(size_t)ep.out * ts + e] = sum;

@@ -27,12 +27,17 @@ namespace dpgo {
 namespace nd {
 
 // ---- device-facing plan records (plain ints, uploaded as they are) ------------------------------------------
+// Records are sized in whole 16-byte words and carry what the kernel needs WITHOUT a second dependent load: the first
+// step of a CTA sits in its (phase, CTA) record, the first four contribution tiles sit in the gather / epilogue record.
 struct Step { int g0, g1, j0, j1, e0, e1, pad0, pad1; };              // ranges into gathers / jobs / epis
-struct Gather { int ytile; int src; int c0, c1; };                     // smem tile <- source tile - sum of contribution tiles
+struct CtaPhase { int s0, s1; int g0, g1, j0, j1, e0, e1; };          // steps [s0, s1) of one CTA in one phase + step s0 inline
+constexpr int INLINE_CONTRIB = 4;
+struct Gather { int ytile; int src; int nc; int cext; int ci[INLINE_CONTRIB]; };   // smem tile <- source tile - sum of nc contribution tiles
 struct Job { long long mat; int ncols; int ycol; int slot; int accum; int pad0, pad1; };   // one warp: panel piece x y
-struct Epi { int kind; int slot0; int nslots; int half; int out; int aux; int c0, c1; };   // one pose (4 rows of a panel)
+struct Epi { int kind; int slot0; int nslots; int half; int out; int aux; int nc; int cext; int ci[INLINE_CONTRIB]; };   // one pose (dh rows of a panel)
 enum EpiKind { EPI_F_OWN = 0, EPI_F_BND = 1, EPI_B_OWN = 2, EPI_ROOT = 3 };
-struct Phase { int dir; int stage; int step_ptr0; int pad; };         // dir 0 forward (source = V, pose ids), 1 backward (source = TX)
+struct Phase { int dir; int stage; int cta0; int pad; };              // dir 0 forward (source = V, pose ids), 1 backward (source = TX); cta0 = first CtaPhase record
+constexpr int MAX_PHASES = 16;
 
 constexpr int PANEL_ROWS = 8;
 
@@ -76,12 +81,12 @@ struct Hierarchy {
 
 struct Plan {
   std::vector<Phase> phases;       // 2 * nstages - 1
-  std::vector<int> cta_step;       // phases * (grid + 1): absolute step indices
+  std::vector<CtaPhase> cta_phase; // phases * grid
   std::vector<Step> steps;
   std::vector<Gather> gathers;
   std::vector<Job> jobs;
   std::vector<Epi> epis;
-  std::vector<int> csrc;           // contribution tile ids
+  std::vector<int> csrc;           // contribution tile ids beyond the INLINE_CONTRIB kept in the records
   int grid = 0, r = 0;
   int max_ytiles = 0, max_slots = 0;
   int64_t bytes_per_apply = 0;     // matrix bytes streamed by one application (all phases)

@@ -217,6 +217,12 @@ DPGO_API int dpgo_debug_phase_latency(dpgo_problem_t *p, int phases, double *us_
  * accumulated milliseconds in ms_by_kind[8] (0 eval pass, 1 dense preconditioner apply, 2 partial sums + projection,
  * 3 Hessian product, 4 tCG update, 5 retraction, 6 final, 7 unused) and resets them; enable == 0 switches it off. */
 DPGO_API int dpgo_debug_phase_times(dpgo_problem_t *p, int enable, double *ms_by_kind);
+/* same with 32 slots: 0..7 as above (1 = the whole exact-preconditioner application when the dense inverse is used),
+ * 8 + k = phase k of the sparse exact preconditioner's application (k < 16), 24 / 25 / 26 = gathers / panel jobs /
+ * epilogues of those phases as seen by CTA 0, others unused */
+DPGO_API int dpgo_debug_phase_times32(dpgo_problem_t *p, int enable, double *ms_by_kind);
+/* same with 64 slots: 32 + 3 k + {0, 1, 2} = gathers / panel jobs / epilogues of phase k (k < 10) as seen by CTA 0 */
+DPGO_API int dpgo_debug_phase_times64(dpgo_problem_t *p, int enable, double *ms_by_kind);
 
 /* ---- boundary-pose exchange (multi-agent, one agent per GPU) ----------------------------- */
 /* ref: PGOAgent::getSharedPoseDict, src/PGOAgent.cpp:95-105: register which local poses are

@@ -22,13 +22,14 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--dataset", default="sphere2500")
     ap.add_argument("--rank", type=int, default=5)
-    ap.add_argument("--precond", default="exact", choices=["exact", "jacobi"])
+    ap.add_argument("--precond", default="exact", choices=["exact", "dense", "jacobi"])
     ap.add_argument("--steps", type=int, default=30)
     args = ap.parse_args()
     edges, n = pg.read_g2o_file(os.path.join(ROOT, "data", args.dataset + ".g2o"))
     d = edges.d
     X0 = pg.fixedStiefelVariable(d, args.rank) @ pg.chordalInitialization(d, n, edges)
-    prob = dp.QuadraticProblem(n, d, args.rank)
+    PRE = {"exact": dp.PRECOND_SPARSE_EXACT, "dense": dp.PRECOND_DENSE_EXACT, "jacobi": dp.PRECOND_BLOCK_JACOBI}[args.precond]
+    prob = dp.QuadraticProblem(n, d, args.rank, preconditioners=(dp.PRECOND_BLOCK_JACOBI, PRE))
     prob.setQ_blocks(*pg.connection_laplacian_blocks(edges))
     prob.set_stream(torch.cuda.current_stream().cuda_stream)
     opt = dp.QuadraticOptimizer(prob)
@@ -36,7 +37,7 @@ def main():
     opt.setTrustRegionIterations(1)
     opt.setTrustRegionMaxInnerIterations(10)
     opt.setTrustRegionInitialRadius(100)
-    opt.setPreconditioner(dp.PRECOND_DENSE_EXACT if args.precond == "exact" else dp.PRECOND_BLOCK_JACOBI)
+    opt.setPreconditioner(PRE)
     X0d = torch.from_numpy(np.asfortranarray(X0).ravel(order="F").copy()).cuda()
 
     def steps(count):
@@ -51,20 +52,27 @@ def main():
         return applies, passes
 
     steps(6)
-    ms = (C.c_double * 8)()
-    _capi.check(prob._lib.dpgo_debug_phase_times(prob._h, 1, ms))
+    ms = (C.c_double * 64)()
+    _capi.check(prob._lib.dpgo_debug_phase_times64(prob._h, 1, ms))
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     torch.cuda.synchronize()
     e0.record()
     applies, passes = steps(args.steps)
     e1.record()
     torch.cuda.synchronize()
-    _capi.check(prob._lib.dpgo_debug_phase_times(prob._h, 0, ms))
+    _capi.check(prob._lib.dpgo_debug_phase_times64(prob._h, 0, ms))
     out = {"workload": f"{args.dataset} 1 agent r={args.rank} {args.precond}", "steps": args.steps,
            "ms_per_step_events": e0.elapsed_time(e1) / args.steps, "precond_applies": applies, "q_passes": passes,
            "ms_per_step_by_kind": {k: ms[i] / args.steps for i, k in enumerate(KINDS) if ms[i] > 0},
            "us_per_dense_apply": 1e3 * ms[1] / max(applies, 1), "us_per_partial_sum": 1e3 * ms[2] / max(applies, 1),
            "us_per_hessian": 1e3 * ms[3] / max(passes - 2 * args.steps, 1)}
+    if args.precond == "exact":
+        out["nd"] = prob.nd_info()
+        out["us_per_apply_by_nd_phase"] = [1e3 * ms[8 + k] / max(applies, 1) for k in range(out["nd"]["phases"])]
+        out["us_per_apply_cta0"] = {"gathers": 1e3 * ms[24] / max(applies, 1), "jobs": 1e3 * ms[25] / max(applies, 1),
+                                    "epilogues": 1e3 * ms[26] / max(applies, 1)}
+        out["us_per_apply_cta0_by_phase"] = [[round(1e3 * ms[32 + 3 * k + q] / max(applies, 1), 3) for q in range(3)]
+                                             for k in range(out["nd"]["phases"])]
     print(json.dumps(out))
 
 
