@@ -76,6 +76,8 @@ SIGNATURES = {
     "dpgo_optimize": (C.c_int, [_vp, C.POINTER(OptParams), _dp, _dp, C.POINTER(OptResult)]),
     "dpgo_problem_upload_X": (C.c_int, [_vp, _dp]),
     "dpgo_problem_download_X": (C.c_int, [_vp, _dp]),
+    "dpgo_problem_upload_X_async": (C.c_int, [_vp, _dp]),
+    "dpgo_problem_download_X_async": (C.c_int, [_vp, _dp]),
     "dpgo_problem_copy_X_from_device": (C.c_int, [_vp, _vp]),
     "dpgo_problem_device_X": (C.c_int, [_vp, C.POINTER(_vp)]),
     "dpgo_problem_device_G": (C.c_int, [_vp, C.POINTER(_vp)]),

@@ -503,8 +503,43 @@ class DistributedPGO:
                 self.selected = [int(np.argmax(per_agent))]           # ref :308-325
         return RoundStats(cost, gn, active)
 
-    # -- the same round through the HOST-level interface (reference protocol: host matrices in and out) -------
+    # -- one round with host buffers in and out (the public host-level call of the runner) ---------------------------
+    def _host_buffers(self):
+        if not hasattr(self, "_hx"):
+            torch = self.torch
+            self._hx, self._hx_keep = {}, {}
+            for a in self.local_ids:
+                ag = self.agents[a]
+                t = torch.empty(((self.d + 1) * ag.n, self.r), dtype=torch.float64).pin_memory()
+                self._hx_keep[a] = t
+                self._hx[a] = t.numpy().T                   # (r, N) Fortran-ordered view of the pinned buffer
+                self._hx[a][...] = ag.X
+        return self._hx
+
     def step_host(self) -> None:
+        """One round with every iterate crossing the host boundary: per local agent X is uploaded from pinned host
+        memory, the public poses are exchanged (pack -> one all-gather -> G rebuild, on the device), the active agents
+        optimise, and their iterates are read back to the host.  ag.X (host) is the state between rounds."""
+        hx = self._host_buffers()
+        for a in self.local_ids:
+            if hx[a] is not self.agents[a].X:
+                hx[a][...] = self.agents[a].X
+            self.agents[a].mProblem.upload_X_async(hx[a])
+        self.exchange()
+        active = self._active()
+        for a in self.local_ids:
+            if a in active:
+                self.agents[a].opt.optimize_resident_async()
+                self.agents[a].mProblem.download_X_async(hx[a])
+        for a in self.local_ids:
+            if a in active:
+                self.agents[a].mProblem.sync()
+                self.agents[a].X = hx[a]
+                self.agents[a].mIterationNumber += 1
+        self.round += 1
+
+    # -- the same round through the HOST-level interface (reference protocol: host matrices in and out) -------
+    def step_host_dict(self) -> None:
         """One round with every iterate crossing the host boundary, as a user of the reference API would drive it:
         getSharedPoseDict -> (all-gather of the host-packed public poses) -> updateNeighborPoses -> iterate(), i.e.
         per active agent H2D of X and G, one persistent kernel, D2H of X.  Used for the end-to-end number."""
@@ -541,10 +576,10 @@ class DistributedPGO:
         self.round += 1
 
     def host_bytes_per_step(self):
-        """(h2d, d2h) bytes one active agent moves per host-level step: X and G in, X out (+ result record)."""
-        a = self.local_ids[0]
-        vb = self.r * (self.d + 1) * int(self.counts[a]) * 8
-        return 2 * vb + self.slot_elems * 8, vb + 112 + self.k * self.slot_elems * 8
+        """(h2d, d2h) bytes this rank moves per step_host round: every local agent's X in, the active agents' X out."""
+        vb = [self.r * (self.d + 1) * int(self.counts[a]) * 8 for a in self.local_ids]
+        nact = max(1, len(self.local_ids) // max(self.ncolours, 1)) if self.schedule == "coloured" else len(self.local_ids)
+        return int(sum(vb)), int(sum(sorted(vb)[-nact:]))
 
     def assemble(self) -> np.ndarray:
         """Gather the full iterate on the host (all local agents; distributed: rank-local block only)."""

@@ -281,6 +281,7 @@ dpgo::nd::Options nd_options(int grid, int r) {
   if (const char *e = std::getenv("DPGO_ND_LEAF")) opt.leaf_size = std::max(1, std::atoi(e));
   if (const char *e = std::getenv("DPGO_ND_TPHASE_US")) opt.t_phase_us = std::atof(e);
   if (const char *e = std::getenv("DPGO_ND_BW_GBS")) opt.bw_gbs = std::atof(e);
+  if (const char *e = std::getenv("DPGO_ND_TTILE_US")) opt.t_tile_us = std::atof(e);
   return opt;
 }
 
@@ -901,6 +902,18 @@ int dpgo_problem_download_X(dpgo_problem_t *p, double *X_host) {
   DPGO_TRY(download_vec(p, dpgo::V_X0, X_host));
   DPGO_CUDA(cudaStreamSynchronize(p->stream));
   return DPGO_OK;
+}
+
+int dpgo_problem_upload_X_async(dpgo_problem_t *p, const double *X_host) {
+  DPGO_CHECK_HANDLE(p);
+  DPGO_REQUIRE(X_host, DPGO_ERR_INVALID_ARG, "null X");
+  return upload_vec(p, dpgo::V_X0, X_host);
+}
+
+int dpgo_problem_download_X_async(dpgo_problem_t *p, double *X_host) {
+  DPGO_CHECK_HANDLE(p);
+  DPGO_REQUIRE(X_host, DPGO_ERR_INVALID_ARG, "null X");
+  return download_vec(p, dpgo::V_X0, X_host);
 }
 
 int dpgo_problem_copy_X_from_device(dpgo_problem_t *p, const double *X_dev) {

@@ -374,20 +374,32 @@ void build_hierarchy(const BsrView &Q, const Options &opt, Hierarchy &H) {
   std::vector<std::vector<int>> at_level((size_t)depth);
   for (int i = 0; i < nt; ++i) at_level[(size_t)T[(size_t)i].level].push_back(i);
   const int dh = Q.dh;
+  // cost of one application in microseconds (measured on B200, sphere2500 and its 8 / 16-agent splits, scripts/phase_times.py):
+  // every phase pays a fixed part (grid barrier + dependent L2 round trips of the gather / job / epilogue stages), a part
+  // proportional to the largest input vector a CTA has to stage (every CTA that works on a node gathers the node's whole
+  // input: own tiles going up, boundary tiles coming down), and its share of the streamed matrix bytes
   auto eval = [&](const std::vector<int> &cuts, double &bytes_out) {
-    double bytes = 0.0;
+    double bytes = 0.0, us = 0.0;
     for (size_t k = 0; k < cuts.size(); ++k) {
       const int c0 = cuts[k], c1 = (k + 1 < cuts.size()) ? cuts[k + 1] : depth;
+      double stage_bytes_f = 0.0, stage_bytes_b = 0.0;
+      int max_own = 0, max_bnd = 0;
       for (int i : at_level[(size_t)c0]) {
         const NdNode &t = T[(size_t)i];
         const int last = std::min<int>((int)t.cum.size() - 1, c1 - 1 - c0);
         const double s = (double)dh * t.cum[(size_t)last], b = (double)dh * t.bnd.size();
-        bytes += (s * (s + b) + s * b) * 8.0;
+        stage_bytes_f += s * (s + b) * 8.0;
+        stage_bytes_b += s * b * 8.0;
+        max_own = std::max(max_own, t.cum[(size_t)last]);
+        max_bnd = std::max(max_bnd, (int)t.bnd.size());
       }
       // leaves of the dissection tree that end above this cut level belong to the fragment of their ancestor: counted there
+      bytes += stage_bytes_f + stage_bytes_b;
+      us += opt.t_phase_us + opt.t_tile_us * max_own + stage_bytes_f / (opt.bw_gbs * 1e3);
+      if (k > 0) us += opt.t_phase_us + opt.t_tile_us * max_bnd + stage_bytes_b / (opt.bw_gbs * 1e3);
     }
     bytes_out = bytes;
-    return (2.0 * cuts.size() - 1.0) * opt.t_phase_us + bytes / (opt.bw_gbs * 1e3);
+    return us;
   };
   struct Cand { std::vector<int> cuts; double cost, bytes; };
   std::vector<Cand> cands;

@@ -49,8 +49,9 @@ struct Options {
   int max_cuts = 3;          // macro levels <= max_cuts + 1
   int ycap_tiles = 600;      // shared-memory capacity for gathered tiles per step
   int slot_cap = 240;        // shared-memory partial-sum slots (8 x r doubles each) per step
-  double t_phase_us = 2.0;   // cost model: one grid-wide phase
-  double bw_gbs = 4000.0;    // cost model: effective streaming bandwidth of the panel products
+  double t_phase_us = 3.5;   // cost model: fixed part of one phase (grid barrier + the stages' dependent L2 round trips)
+  double t_tile_us = 0.012;  // cost model: staging one tile of a phase's largest input vector (per CTA, redundant over CTAs)
+  double bw_gbs = 3000.0;    // cost model: effective streaming bandwidth of the panel products
   int force_ncuts = -1;      // >= 0: use exactly this many cuts (tests)
   double shift = 0.1;
 };

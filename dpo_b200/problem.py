@@ -204,6 +204,13 @@ class QuadraticProblem:
         capi.check(self._lib.dpgo_problem_download_X(self._h, capi.dptr(out)))
         return out
 
+    def upload_X_async(self, Xf: np.ndarray) -> None:
+        """Xf: Fortran-contiguous (r, N) float64 (pinned for a truly asynchronous copy); no synchronisation."""
+        capi.check(self._lib.dpgo_problem_upload_X_async(self._h, capi.dptr(Xf)))
+
+    def download_X_async(self, out: np.ndarray) -> None:
+        capi.check(self._lib.dpgo_problem_download_X_async(self._h, capi.dptr(out)))
+
     def copy_X_from_device(self, src_ptr: int) -> None:
         capi.check(self._lib.dpgo_problem_copy_X_from_device(self._h, C.c_void_p(src_ptr)))
 
@@ -222,6 +229,10 @@ class QuadraticProblem:
 
     def spmv_algorithmic_bytes(self, add_G: bool = False) -> int:
         return int(self._lib.dpgo_spmv_algorithmic_bytes(self._h, int(add_G)))
+
+    def nd_ready(self) -> bool:
+        """True once the sparse exact preconditioner was requested for this problem (its hierarchy can be queried)."""
+        return bool(self._precond_mask & (1 << PRECOND_SPARSE_EXACT))
 
     def nd_info(self) -> dict:
         """Diagnostics of the sparse exact preconditioner's hierarchy (prepares it if needed)."""

@@ -174,6 +174,10 @@ DPGO_API int dpgo_optimize(dpgo_problem_t *p, const dpgo_opt_params_t *params, c
 /* ---- device-resident path (iterate lives in HBM between calls) --------------------------- */
 DPGO_API int dpgo_problem_upload_X(dpgo_problem_t *p, const double *X_host);
 DPGO_API int dpgo_problem_download_X(dpgo_problem_t *p, double *X_host);
+/* the same without the closing synchronisation (pinned host buffers; order with dpgo_problem_sync): one round of a
+ * multi-agent run = upload_X_async, exchange, optimize_resident_async, download_X_async, sync */
+DPGO_API int dpgo_problem_upload_X_async(dpgo_problem_t *p, const double *X_host);
+DPGO_API int dpgo_problem_download_X_async(dpgo_problem_t *p, double *X_host);
 /* resident iterate <- device buffer (asynchronous device-to-device copy on the handle's stream) */
 DPGO_API int dpgo_problem_copy_X_from_device(dpgo_problem_t *p, const double *X_dev);
 DPGO_API int dpgo_problem_device_X(dpgo_problem_t *p, double **X_dev);     /* r x (d+1)n, read/write */

@@ -879,12 +879,22 @@ class RBCDTrace:
 
 
 class MultiRobotDriver:
-    """Serial simulation of k agents with greedy selection.  ref: examples/MultiRobotExample.cpp:21-340."""
+    """Serial simulation of k agents.  ref: examples/MultiRobotExample.cpp:21-340.
+
+    schedule = "greedy"   the reference driver: one agent per iteration, argmax of the block gradient norms (:308-325);
+             = "coloured" all agents of one colour class of the agent graph per round (greedy colouring in agent
+                          order); agents of one colour share no edge, so the round equals |class| sequential RBCD
+                          steps of the reference in any order -- the concurrent schedule of the multi-GPU runner;
+             = "parallel" every agent every round on the neighbours' poses of the previous round (Jacobi).
+    """
 
     def __init__(self, meas: Measurements, n: int, k: int, r: int = 5,
                  algorithm: int = QuadraticOptimizer.RTR, precond: str = "exact",
                  owner: Optional[np.ndarray] = None, T_init: Optional[np.ndarray] = None,
-                 acceleration: bool = False):
+                 acceleration: bool = False, schedule: str = "greedy"):
+        assert schedule in ("greedy", "coloured", "parallel")
+        self.schedule = schedule
+        self.round = 0
         self.meas, self.n, self.k, self.r, self.d = meas, n, k, r, meas.d
         self.owner = contiguous_partition(n, k) if owner is None else owner
         parts, counts, glob = split_measurements(meas, self.owner, k)
@@ -906,6 +916,15 @@ class MultiRobotDriver:
                 ag.initialize_acceleration()                                            # ref setX -> :60-62
         self.selected = 0
         self.trace = RBCDTrace()
+        # greedy colouring of the agent graph in agent order (same rule as dpo_b200.agent.ExchangePlan.colouring)
+        self.colour = [-1] * k
+        for a in range(k):
+            used = {self.colour[b] for b in self.agents[a].neighbors if self.colour[b] >= 0}
+            c = 0
+            while c in used:
+                c += 1
+            self.colour[a] = c
+        self.ncolours = max(self.colour) + 1
 
     def assemble(self) -> np.ndarray:
         dh = self.d + 1
@@ -915,8 +934,36 @@ class MultiRobotDriver:
             X[:, cols] = ag.X
         return X
 
+    def _step_concurrent(self) -> Tuple[float, float]:
+        """One round of the coloured / parallel schedule: every active agent sees its neighbours' poses as they were
+        at the start of the round (one exchange per round), then all active agents take their step."""
+        if self.schedule == "coloured":
+            active = [a for a in range(self.k) if self.colour[a] == self.round % self.ncolours]
+        else:
+            active = list(range(self.k))
+        shared = [ag.get_shared_pose_dict() for ag in self.agents]
+        aux = [ag.get_aux_shared_pose_dict() if ag.acceleration else None for ag in self.agents]
+        for a in active:
+            for b in self.agents[a].neighbors:
+                self.agents[a].update_neighbor_poses(b, shared[b])
+                if self.agents[a].acceleration:
+                    self.agents[a].update_aux_neighbor_poses(b, aux[b])
+        for a, ag in enumerate(self.agents):
+            ag.iterate(a in active)
+        self.round += 1
+        X = self.assemble()
+        RG = self.central.rie_grad(X)
+        gn = float(np.linalg.norm(RG))
+        cost = 2.0 * self.central.f(X)
+        self.trace.cost.append(cost)
+        self.trace.gradnorm.append(gn)
+        self.trace.selected.append(active[0] if active else -1)
+        return cost, gn
+
     def step(self) -> Tuple[float, float]:
         """One outer iteration.  ref: examples/MultiRobotExample.cpp:229-334."""
+        if self.schedule != "greedy":
+            return self._step_concurrent()
         sel = self.agents[self.selected]
         for ag in self.agents:
             if ag.id != sel.id:

@@ -24,10 +24,19 @@ def main():
     ap.add_argument("--rank", type=int, default=5)
     ap.add_argument("--precond", default="exact", choices=["exact", "dense", "jacobi"])
     ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--agents", type=int, default=1, help="> 1: the private sub-graph of agent 0 of a contiguous split")
     args = ap.parse_args()
     edges, n = pg.read_g2o_file(os.path.join(ROOT, "data", args.dataset + ".g2o"))
     d = edges.d
     X0 = pg.fixedStiefelVariable(d, args.rank) @ pg.chordalInitialization(d, n, edges)
+    if args.agents > 1:
+        from dpo_b200.agent import contiguous_owner, partition_edges
+        from dpo_b200.posegraph import EdgeSet
+        owner = contiguous_owner(n, args.agents)
+        parts, counts, glob = partition_edges(edges, owner, args.agents)
+        edges = EdgeSet.join([parts[0][0], parts[0][1]])
+        n = int(counts[0])
+        X0 = X0[:, :(d + 1) * n]
     PRE = {"exact": dp.PRECOND_SPARSE_EXACT, "dense": dp.PRECOND_DENSE_EXACT, "jacobi": dp.PRECOND_BLOCK_JACOBI}[args.precond]
     prob = dp.QuadraticProblem(n, d, args.rank, preconditioners=(dp.PRECOND_BLOCK_JACOBI, PRE))
     prob.setQ_blocks(*pg.connection_laplacian_blocks(edges))
@@ -61,7 +70,7 @@ def main():
     e1.record()
     torch.cuda.synchronize()
     _capi.check(prob._lib.dpgo_debug_phase_times64(prob._h, 0, ms))
-    out = {"workload": f"{args.dataset} 1 agent r={args.rank} {args.precond}", "steps": args.steps,
+    out = {"workload": f"{args.dataset} agent 0 of {args.agents} ({n} poses) r={args.rank} {args.precond}", "steps": args.steps,
            "ms_per_step_events": e0.elapsed_time(e1) / args.steps, "precond_applies": applies, "q_passes": passes,
            "ms_per_step_by_kind": {k: ms[i] / args.steps for i, k in enumerate(KINDS) if ms[i] > 0},
            "us_per_dense_apply": 1e3 * ms[1] / max(applies, 1), "us_per_partial_sum": 1e3 * ms[2] / max(applies, 1),

@@ -14,6 +14,8 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 DATASETS = ["CSAIL", "grid3D", "parking-garage", "smallGrid3D", "sphere2500", "torus3D"]
 LINES = 400
+# final rounded trajectories X[:, :d]^T X the reference ships (result/opt_pose/NP<dataset>.csv, d x (d+1)n), copied whole
+OPT_POSE = ["parking-garage"]
 
 
 def main():
@@ -34,6 +36,18 @@ def main():
         else:
             with open(dst, "w") as fh:
                 fh.write(head)
+            print(f"wrote {dst}")
+    for ds in OPT_POSE:
+        src = os.path.join(args.reference, "result", "opt_pose", f"NP{ds}.csv")
+        dst = os.path.join(HERE, f"NP{ds}_opt_pose.csv")
+        body = open(src).read()
+        if args.check:
+            same = os.path.exists(dst) and open(dst).read() == body
+            print(f"{ds} opt_pose: {'identical' if same else 'DIFFERS'}")
+            bad += 0 if same else 1
+        else:
+            with open(dst, "w") as fh:
+                fh.write(body)
             print(f"wrote {dst}")
     sys.exit(1 if bad else 0)
 

@@ -15,7 +15,8 @@ def load(ds, data_dir):
     return pg.read_g2o_file(os.path.join(data_dir, ds + ".g2o"))
 
 
-@pytest.mark.parametrize("ds,iters", [("smallGrid3D", 120), ("sphere2500", 50), ("torus3D", 30), ("CSAIL", 40)])
+@pytest.mark.parametrize("ds,iters", [("smallGrid3D", 120), ("sphere2500", 50), ("torus3D", 30), ("CSAIL", 40), ("grid3D", 25),
+                                      ("parking-garage", 25)])
 def test_greedy_schedule_reproduces_golden_trace(ds, iters, data_dir, golden_dir):
     from dpo_b200.agent import DistributedPGO
     edges, n = load(ds, data_dir)
@@ -26,8 +27,67 @@ def test_greedy_schedule_reproduces_golden_trace(ds, iters, data_dir, golden_dir
         st = run.step()
         cost.append(st.cost)
         gn.append(st.gradnorm)
-    assert np.max(np.abs(np.array(cost) - gold[:, 0]) / gold[:, 0]) <= 5e-9
-    assert np.max(np.abs(np.array(gn) - gold[:, 1]) / gold[:, 1]) <= 5e-8
+    # parking-garage is ill-conditioned (kappa ~ 2, tau ~ 1: every tCG solve runs to its 10-iteration cap), so the
+    # summation-order differences of the device-side G assembly are amplified above the print precision of the trace
+    ctol, gtol = (5e-8, 5e-6) if ds == "parking-garage" else (5e-9, 5e-8)
+    assert np.max(np.abs(np.array(cost) - gold[:, 0]) / gold[:, 0]) <= ctol
+    assert np.max(np.abs(np.array(gn) - gold[:, 1]) / gold[:, 1]) <= gtol
+
+
+@pytest.mark.parametrize("ds,k,rounds", [("torus3D", 8, 10), ("parking-garage", 4, 8), ("sphere2500", 8, 8)])
+def test_coloured_schedule_matches_oracle(ds, k, rounds, data_dir):
+    """The schedule the multi-GPU benchmark runs (BASELINE configs 3 and 4 and the sphere2500 scaling workload): k
+    agents, coloured RBCD, exact preconditioner -- per-round central cost / gradient norm and the iterates against the
+    oracle's coloured driver (<= 1e-8 relative)."""
+    from dpo_b200.agent import DistributedPGO
+    edges, n = load(ds, data_dir)
+    meas, _ = orc.read_g2o(os.path.join(data_dir, ds + ".g2o"))
+    run = DistributedPGO(edges, n, k, r=5, schedule="coloured")
+    drv = orc.MultiRobotDriver(meas, n, k, r=5, schedule="coloured")
+    assert run.colour == drv.colour
+    # (parking-garage: ill-conditioned -- kappa ~ 2, tau ~ 1, every tCG solve hits its cap -- rounding differences are amplified)
+    ctol, gtol, xtol = (1e-7, 1e-5, 1e-5) if ds == "parking-garage" else (1e-8, 1e-7, 1e-8)
+    for _ in range(rounds):
+        st = run.step()
+        cost, gn = drv.step()
+        assert abs(st.cost - cost) <= ctol * abs(cost)
+        assert abs(st.gradnorm - gn) <= gtol * gn
+    Xg, Xo = run.assemble(), drv.assemble()
+    assert np.linalg.norm(Xg - Xo) <= xtol * np.linalg.norm(Xo)
+
+
+def test_final_trajectory_parking_garage(data_dir, golden_dir):
+    """The reference's shipped final trajectory (result/opt_pose/NPparking-garage.csv) through the device-resident
+    5-agent greedy runner; tolerance as in tests/test_oracle_golden.py."""
+    from dpo_b200.agent import DistributedPGO
+    edges, n = load("parking-garage", data_dir)
+    run = DistributedPGO(edges, n, 5, r=5, schedule="greedy")
+    for _ in range(450):
+        run.step()
+    X = run.assemble()
+    T = X[:, :edges.d].T @ X
+    ref = np.loadtxt(os.path.join(golden_dir, "NPparking-garage_opt_pose.csv"), delimiter=",")
+    assert np.abs(T - ref).max() <= 5e-4
+
+
+def test_host_level_round_equals_resident_round(data_dir):
+    """DistributedPGO.step_host (X from / to pinned host memory every round) == the device-resident rounds, bit for bit;
+    step_host_dict (the reference's PoseDict protocol on the host) agrees to rounding."""
+    from dpo_b200.agent import DistributedPGO
+    edges, n = load("smallGrid3D", data_dir)
+    runs = [DistributedPGO(edges, n, 5, r=5, schedule="coloured") for _ in range(3)]
+    for _ in range(6):
+        runs[0].step(evaluate=False)
+        runs[1].step_host()
+        runs[2].step_host_dict()
+    X0 = runs[0].assemble()
+    dh = edges.d + 1
+    for q, tol in ((1, 0.0), (2, 1e-11)):
+        Xh = np.zeros_like(X0)
+        for a, ag in runs[q].agents.items():
+            cols = (runs[q].glob[a][:, None] * dh + np.arange(dh)[None, :]).ravel()
+            Xh[:, cols] = ag.X
+        assert np.linalg.norm(Xh - X0) <= tol * np.linalg.norm(X0)
 
 
 def test_device_G_matches_host_G(data_dir):

@@ -84,6 +84,30 @@ def test_rtr_single_step_sequence(ds, r, precond, data_dir):
         assert res.f_opt <= res.f_init            # ref: assert(result.fOpt <= result.fInit)
 
 
+def test_bitwise_reproducible(data_dir):
+    """Fixed summation orders everywhere (no floating-point atomics; SURVEY section 7, hard part 5): two independent
+    runs of the same RTR sequence give bit-identical iterates and tCG decisions -- also a check that no phase of the
+    persistent kernel reads data another CTA is still writing."""
+    import dpo_b200 as dp
+    outs = []
+    for rep in range(2):
+        op, gp, X0 = setup("sphere2500", 5, data_dir)
+        go = dp.QuadraticOptimizer(gp)
+        go.setTrustRegionTolerance(1e-2)
+        go.setTrustRegionIterations(1)
+        go.setTrustRegionMaxInnerIterations(10)
+        go.setTrustRegionInitialRadius(100)
+        X, log = X0, []
+        for _ in range(6):
+            X = go.optimize(X)
+            res = go.getOptResult()
+            log.append((res.tcg_iterations, res.tcg_status, res.f_opt, res.gradnorm_opt))
+        outs.append((np.array(X), log))
+        gp.close()
+    assert outs[0][1] == outs[1][1]
+    assert np.array_equal(outs[0][0], outs[1][0])
+
+
 @pytest.mark.parametrize("ds,expect", [("tinyGrid3D", 18.51936666), ("sphere2500", 1687.00588)])
 def test_local_pose_graph_optimization(ds, expect, data_dir):
     """SingleRobotExample path (ref examples/SingleRobotExample.cpp:89-103, src/PGOAgent.cpp:964-990):

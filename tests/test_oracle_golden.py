@@ -42,6 +42,46 @@ def test_golden_traces(ds, iters, data_dir, golden_dir):
     assert np.max(np.abs(np.array(tr.gradnorm) - gold[:, 1]) / gold[:, 1]) <= 5e-9
 
 
+def test_grid3D_golden_trace(data_dir, golden_dir):
+    """result/graph/NPgrid3D.txt (8000 poses, 5 agents of 1600): the largest shipped trace."""
+    meas, n = load("grid3D", data_dir)
+    drv = orc.MultiRobotDriver(meas, n, 5, r=5)
+    tr = drv.run(12)
+    gold = np.loadtxt(os.path.join(golden_dir, "NPgrid3D_head400.txt"), delimiter=",")[:12]
+    assert np.max(np.abs(np.array(tr.cost) - gold[:, 0]) / gold[:, 0]) <= 5e-9
+    assert np.max(np.abs(np.array(tr.gradnorm) - gold[:, 1]) / gold[:, 1]) <= 5e-9
+
+
+def test_final_trajectory_parking_garage(data_dir, golden_dir):
+    """result/opt_pose/NPparking-garage.csv: X[:, :d]^T X after the reference's 1000-iteration
+    5-agent run.  The run plateaus after ~400 iterations (every agent's local gradient norm is below the 1e-2 early
+    exit, src/QuadraticOptimizer.cpp:67-70); translations are O(10..100) m, so 5e-4 absolute is ~1e-5 relative."""
+    meas, n = load("parking-garage", data_dir)
+    drv = orc.MultiRobotDriver(meas, n, 5, r=5)
+    drv.run(450)
+    X = drv.assemble()
+    T = X[:, :meas.d].T @ X
+    ref = np.loadtxt(os.path.join(golden_dir, "NPparking-garage_opt_pose.csv"), delimiter=",")
+    assert ref.shape == T.shape
+    assert np.abs(T - ref).max() <= 5e-4
+
+
+def test_coloured_schedule_is_sequential_rbcd(data_dir):
+    """The coloured schedule (agents of one colour class step concurrently on the poses of the round start) equals
+    the same agents stepping one after the other in any order: same-colour agents share no edge."""
+    meas, n = load("smallGrid3D", data_dir)
+    a = orc.MultiRobotDriver(meas, n, 5, r=5, schedule="coloured")
+    b = orc.MultiRobotDriver(meas, n, 5, r=5, schedule="greedy")
+    assert a.ncolours == 2 and a.colour == [0, 1, 0, 1, 0]
+    for rnd in range(4):
+        a.step()
+        for ag_id in [q for q in range(5) if a.colour[q] == rnd % 2][::-1]:     # reversed order on purpose
+            b.selected = ag_id
+            b.step()
+        assert np.abs(a.assemble() - b.assemble()).max() <= 1e-13
+    assert all(np.diff(a.trace.cost) <= 1e-9)
+
+
 def test_single_robot_known_answers(data_dir):
     """SingleRobotExample Cost = 18.51936666 (3 outer / 29 inner) on tinyGrid3D."""
     cost, res, _ = orc.single_robot_example(os.path.join(data_dir, "tinyGrid3D.g2o"))
