@@ -95,6 +95,12 @@ SIGNATURES = {
     "dpgo_debug_phase_times": (C.c_int, [_vp, C.c_int, _dp]),
     "dpgo_debug_phase_times32": (C.c_int, [_vp, C.c_int, _dp]),
     "dpgo_debug_phase_times64": (C.c_int, [_vp, C.c_int, _dp]),
+    "dpgo_device_set": (C.c_int, [C.c_int]),
+    "dpgo_device_malloc": (C.c_int, [C.c_int, C.c_size_t, C.POINTER(_vp)]),
+    "dpgo_device_free": (C.c_int, [C.c_int, _vp]),
+    "dpgo_stream_create": (C.c_int, [C.c_int, C.POINTER(_vp)]),
+    "dpgo_stream_destroy": (C.c_int, [C.c_int, _vp]),
+    "dpgo_stream_synchronize": (C.c_int, [C.c_int, _vp]),
     "dpgo_agent_set_public_poses": (C.c_int, [_vp, C.c_int, _ip]),
     "dpgo_agent_pack_public": (C.c_int, [_vp, _vp]),
     "dpgo_agent_set_shared_edges": (C.c_int, [_vp, C.c_int, _ip, _ip, _ip, _dp, _dp]),

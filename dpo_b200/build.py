@@ -73,12 +73,13 @@ def build_library(force: bool = False, verbose: bool = False) -> str:
 # ---------------------------------------------------------------------------------------------------
 HOST_DIR = os.path.join(HERE, "host")
 HOST_SOURCES = ["DPGO_utils.cpp", "DPGO_robust.cpp", "QuadraticProblem.cpp", "QuadraticOptimizer.cpp", "PGOLogger.cpp",
-                "PGOAgent.cpp"]
+                "PGOAgent.cpp", "DeviceRBCD.cpp"]
+CUDA_INC = os.path.join(os.path.dirname(os.path.dirname(NVCC)), "include")     # nccl.h includes cuda_runtime.h (types only)
 HOST_LIB = os.path.join(LIBDIR, "libDPGO.so")
 INCLUDE = os.path.join(HERE, "..", "include")
 CXX = os.environ.get("CXX", "g++")
 CXXFLAGS = ["-O2", "-std=c++17", "-fPIC", "-Wall", "-Wno-sign-compare", "-Wno-unused-parameter",
-            "-I", os.path.join(INCLUDE, "eigen_shim"), "-I", INCLUDE]
+            "-I", os.path.join(INCLUDE, "eigen_shim"), "-I", INCLUDE, "-I", CUDA_INC]
 
 
 def build_host(force: bool = False) -> str:
@@ -101,7 +102,7 @@ def build_host(force: bool = False) -> str:
 
     with ThreadPoolExecutor(max_workers=6) as ex:
         objs = list(ex.map(compile_one, srcs))
-    res = subprocess.run([CXX, "-shared", "-o", HOST_LIB] + objs + ["-L", LIBDIR, "-ldpgo_b200", "-Wl,-rpath,$ORIGIN", "-lpthread"],
+    res = subprocess.run([CXX, "-shared", "-o", HOST_LIB] + objs + ["-L", LIBDIR, "-ldpgo_b200", "-lnccl", "-Wl,-rpath,$ORIGIN", "-lpthread"],
                          capture_output=True, text=True)
     if res.returncode != 0:
         raise RuntimeError(f"link failed:\n{res.stderr}")
@@ -117,7 +118,7 @@ def build_cpp_program(sources, output, defines=(), extra_includes=()):
         cmd += ["-I", inc]
     for dname in defines:
         cmd += ["-D" + dname]
-    cmd += list(sources) + ["-o", output, "-L", LIBDIR, "-lDPGO", "-ldpgo_b200", "-Wl,-rpath," + LIBDIR, "-lpthread"]
+    cmd += list(sources) + ["-o", output, "-L", LIBDIR, "-lDPGO", "-ldpgo_b200", "-lnccl", "-Wl,-rpath," + LIBDIR, "-lpthread"]
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:
         raise RuntimeError(f"compile failed for {sources}:\n{res.stderr[-4000:]}")

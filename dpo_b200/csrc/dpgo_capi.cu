@@ -86,7 +86,7 @@ struct dpgo_problem {
   // exchange
   int num_public = 0;
   int *d_public = nullptr;
-  int num_edges = 0, num_shared_poses = 0;
+  int num_edges = 0, num_shared_poses = 0, max_slot = -1;
   int *d_pose_ids = nullptr, *d_pose_ptr = nullptr, *d_edge_slot = nullptr, *d_edge_out = nullptr;
   double *d_edge_T = nullptr, *d_edge_om = nullptr;
 
@@ -223,7 +223,7 @@ int ensure_dense(dpgo_problem *p) {
   if (p->dense_per > dpgo::DENSE_PER_MAX)
     return fail(DPGO_ERR_UNSUPPORTED, "dense exact preconditioner: N too large for the per-CTA slab; use block-Jacobi");
   DPGO_CUDA(cudaMalloc(&p->d_dense_part, sizeof(double) * (size_t)p->grid * p->r * N));
-  DPGO_CUDA(cudaMemset(p->d_dense_part, 0, sizeof(double) * (size_t)p->grid * p->r * N));
+  DPGO_CUDA(cudaMemsetAsync(p->d_dense_part, 0, sizeof(double) * (size_t)p->grid * p->r * N, p->stream));
   DPGO_CUDA(cudaMalloc(&p->d_pinv, N * N * sizeof(double)));
   DPGO_CUDA(cudaMemsetAsync(p->d_pinv, 0, N * N * sizeof(double), p->stream));
   cudaError_t e = dpgo::launch_bsr_to_dense(p->n, p->dh, p->nb, p->d_rowptr, p->d_bcol, p->d_bval, 0.1, p->d_pinv, p->N,
@@ -246,7 +246,7 @@ int ensure_dense(dpgo_problem *p) {
     DPGO_CUDA(cudaMalloc(&p->d_sym_cfirst, sizeof(int) * plan.cfirst.size()));
     DPGO_CUDA(cudaMalloc(&p->d_sym_ccount, sizeof(int) * plan.ccount.size()));
     DPGO_CUDA(cudaMalloc(&p->d_dense_t2, sizeof(double) * (size_t)nseg * p->r * N));
-    DPGO_CUDA(cudaMemset(p->d_dense_t2, 0, sizeof(double) * (size_t)nseg * p->r * N));
+    DPGO_CUDA(cudaMemsetAsync(p->d_dense_t2, 0, sizeof(double) * (size_t)nseg * p->r * N, p->stream));
     DPGO_CUDA(cudaMalloc(&p->d_sym_off, sizeof(long long) * plan.off.size()));
     DPGO_CUDA(cudaMalloc(&p->d_ppack, sizeof(double) * (size_t)plan.off[(size_t)nchunks]));
     DPGO_CUDA(cudaMemcpy(p->d_sym_off, plan.off.data(), sizeof(long long) * plan.off.size(), cudaMemcpyHostToDevice));
@@ -677,7 +677,11 @@ int dpgo_problem_set_Q_csr(dpgo_problem_t *p, int nrows, const int32_t *rowptr, 
                            const double *values, unsigned precond_mask) {
   DPGO_CHECK_HANDLE(p);
   DPGO_REQUIRE(nrows == p->N, DPGO_ERR_INVALID_ARG, "Q must be (d+1)n x (d+1)n");
-  DPGO_REQUIRE(rowptr && (rowptr[nrows] == 0 || (colind && values)), DPGO_ERR_INVALID_ARG, "null CSR arrays");
+  DPGO_REQUIRE(rowptr, DPGO_ERR_INVALID_ARG, "null CSR row pointer");
+  DPGO_REQUIRE(rowptr[0] == 0, DPGO_ERR_INVALID_ARG, "CSR row pointer must start at 0");
+  for (int i = 0; i < nrows; ++i)
+    if (rowptr[i + 1] < rowptr[i]) return fail(DPGO_ERR_INVALID_ARG, "CSR row pointer is not non-decreasing");
+  DPGO_REQUIRE(rowptr[nrows] == 0 || (colind && values), DPGO_ERR_INVALID_ARG, "null CSR arrays");
   const int dh = p->dh;
   std::vector<BlockTriplet> trip;
   trip.reserve((size_t)rowptr[nrows] / (dh * dh) + 16);
@@ -1130,6 +1134,43 @@ int dpgo_nd_debug_emulate(int n, int d, int r, int64_t nb, const int32_t *brow, 
   return DPGO_OK;
 }
 
+// ---- plain device helpers ----------------------------------------------------------------------
+int dpgo_device_set(int device) {
+  DPGO_CUDA(cudaSetDevice(device));
+  return DPGO_OK;
+}
+int dpgo_device_malloc(int device, size_t bytes, void **ptr) {
+  DPGO_REQUIRE(ptr, DPGO_ERR_INVALID_ARG, "null argument");
+  *ptr = nullptr;
+  DPGO_CUDA(cudaSetDevice(device));
+  DPGO_CUDA(cudaMalloc(ptr, std::max<size_t>(bytes, 8)));
+  DPGO_CUDA(cudaMemset(*ptr, 0, std::max<size_t>(bytes, 8)));
+  return DPGO_OK;
+}
+int dpgo_device_free(int device, void *ptr) {
+  DPGO_CUDA(cudaSetDevice(device));
+  if (ptr) DPGO_CUDA(cudaFree(ptr));
+  return DPGO_OK;
+}
+int dpgo_stream_create(int device, void **cuda_stream) {
+  DPGO_REQUIRE(cuda_stream, DPGO_ERR_INVALID_ARG, "null argument");
+  DPGO_CUDA(cudaSetDevice(device));
+  cudaStream_t s;
+  DPGO_CUDA(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+  *cuda_stream = (void *)s;
+  return DPGO_OK;
+}
+int dpgo_stream_destroy(int device, void *cuda_stream) {
+  DPGO_CUDA(cudaSetDevice(device));
+  if (cuda_stream) DPGO_CUDA(cudaStreamDestroy((cudaStream_t)cuda_stream));
+  return DPGO_OK;
+}
+int dpgo_stream_synchronize(int device, void *cuda_stream) {
+  DPGO_CUDA(cudaSetDevice(device));
+  DPGO_CUDA(cudaStreamSynchronize((cudaStream_t)cuda_stream));
+  return DPGO_OK;
+}
+
 // ---- boundary-pose exchange --------------------------------------------------------------------
 int dpgo_agent_set_public_poses(dpgo_problem_t *p, int num_public, const int32_t *public_pose) {
   DPGO_CHECK_HANDLE(p);
@@ -1183,6 +1224,8 @@ int dpgo_agent_set_shared_edges(dpgo_problem_t *p, int num_edges, const int32_t 
   free_dev(p->d_edge_T); free_dev(p->d_edge_om);
   p->num_edges = num_edges;
   p->num_shared_poses = (int)pose_ids.size();
+  p->max_slot = -1;
+  for (int e = 0; e < num_edges; ++e) p->max_slot = std::max(p->max_slot, (int)nbr_slot[e]);
   if (num_edges) {
     DPGO_CUDA(cudaMalloc(&p->d_pose_ids, sizeof(int) * pose_ids.size()));
     DPGO_CUDA(cudaMalloc(&p->d_pose_ptr, sizeof(int) * pose_ptr.size()));
@@ -1203,7 +1246,8 @@ int dpgo_agent_set_shared_edges(dpgo_problem_t *p, int num_edges, const int32_t 
 int dpgo_agent_build_G(dpgo_problem_t *p, const double *gathered_dev, int64_t num_slots) {
   DPGO_CHECK_HANDLE(p);
   DPGO_REQUIRE(gathered_dev || p->num_edges == 0, DPGO_ERR_INVALID_ARG, "null gathered buffer");
-  (void)num_slots;
+  DPGO_REQUIRE((int64_t)p->max_slot < num_slots || p->num_edges == 0, DPGO_ERR_INVALID_ARG,
+               "a shared edge refers to a slot beyond the gathered buffer (exchange plan / slot table mismatch)");
   DPGO_CUDA(cudaMemsetAsync(p->d_G, 0, p->vec_bytes(), p->stream));
   if (p->num_edges)
     DPGO_CUDA(dpgo::launch_build_G(p->r, p->dh, p->num_shared_poses, p->d_pose_ids, p->d_pose_ptr, p->d_edge_slot,

@@ -6,6 +6,10 @@
 #include <cstdlib>
 #include <stdexcept>
 
+#include <map>
+#include <memory>
+#include <tuple>
+
 #include "dpgo_b200.h"
 
 namespace DPGO {
@@ -127,32 +131,49 @@ Matrix QuadraticProblem::PreConditioner(const Matrix &Y, const Matrix &Vin) cons
 
 // ---- LiftedSEManifold (ref src/manifold/LiftedSEManifold.cpp:34-45) ------------------------------------
 namespace {
+// One device scratch problem per (n, d, r, device) and thread, created on first use and kept: the manifold operations
+// sit on the Nesterov per-iteration path (PGOAgent::updateY / updateV call project() for every agent and iterate),
+// where creating and destroying a handle per call would mean ~16 cudaMalloc / cudaFree with device-wide syncs.
 struct ScratchProblem {
   dpgo_problem *h = nullptr;
-  ScratchProblem(size_t n, size_t d, size_t r) {
-    check(dpgo_problem_create((int)n, (int)d, (int)r, QuadraticProblem::defaultDevice(), &h), "dpgo_problem_create");
+  ScratchProblem(size_t n, size_t d, size_t r, int device) {
+    check(dpgo_problem_create((int)n, (int)d, (int)r, device, &h), "dpgo_problem_create");
   }
   ~ScratchProblem() { dpgo_problem_destroy(h); }
+  ScratchProblem(const ScratchProblem &) = delete;
+  ScratchProblem &operator=(const ScratchProblem &) = delete;
 };
+struct ScratchRef { dpgo_problem *h; };
+ScratchRef scratch(size_t n, size_t d, size_t r) {
+  static thread_local std::map<std::tuple<size_t, size_t, size_t, int>, std::unique_ptr<ScratchProblem>> cache;
+  const int device = QuadraticProblem::defaultDevice();
+  auto key = std::make_tuple(n, d, r, device);
+  auto it = cache.find(key);
+  if (it == cache.end()) {
+    if (cache.size() >= 8) cache.clear();              // bounded: the agents of one process share few shapes
+    it = cache.emplace(key, std::unique_ptr<ScratchProblem>(new ScratchProblem(n, d, r, device))).first;
+  }
+  return ScratchRef{it->second->h};
+}
 }  // namespace
 
 Matrix LiftedSEManifold::project(const Matrix &M) const {
   assert(M.rows() == (int)r_ && M.cols() == (int)((d_ + 1) * n_));
-  ScratchProblem sp(n_, d_, r_);
+  ScratchRef sp = scratch(n_, d_, r_);
   Matrix out(M.rows(), M.cols());
   check(dpgo_manifold_project(sp.h, M.data(), out.data()), "dpgo_manifold_project");
   return out;
 }
 
 Matrix LiftedSEManifold::tangentProject(const Matrix &X, const Matrix &Z) const {
-  ScratchProblem sp(n_, d_, r_);
+  ScratchRef sp = scratch(n_, d_, r_);
   Matrix out(X.rows(), X.cols());
   check(dpgo_manifold_tangent_project(sp.h, X.data(), Z.data(), out.data()), "dpgo_manifold_tangent_project");
   return out;
 }
 
 Matrix LiftedSEManifold::retract(const Matrix &X, const Matrix &eta) const {
-  ScratchProblem sp(n_, d_, r_);
+  ScratchRef sp = scratch(n_, d_, r_);
   Matrix out(X.rows(), X.cols());
   check(dpgo_manifold_retract(sp.h, X.data(), eta.data(), out.data()), "dpgo_manifold_retract");
   return out;

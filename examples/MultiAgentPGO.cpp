@@ -1,7 +1,11 @@
 // MultiAgentPGO -- command-line driver of the B200 distributed pose-graph optimiser (C++ host API).
 //
 //   MultiAgentPGO <file.g2o> [--robots K] [--iters N] [--stop GRADNORM] [--accel] [--rgd] [--jacobi]
-//                 [--rank R] [--trace out.csv]
+//                 [--rank R] [--trace out.csv] [--resident [--gpus N] [--schedule greedy|coloured|parallel] [--bench ROUNDS]]
+//
+// --resident runs the device-resident multi-GPU runner (DPGO::DeviceRBCD): iterates stay in HBM, K agents over N GPUs
+// of this node, ONE ncclAllGather of the public poses per round; --bench times ROUNDS rounds without the central
+// evaluation.
 //
 // Splits the pose graph into K contiguous agents, initialises every agent from the centralised chordal
 // relaxation lifted to rank R, then runs synchronous Riemannian block-coordinate descent with greedy agent
@@ -9,6 +13,7 @@
 // the trace is "iteration,agent,2f,gradnorm".  Same protocol as the reference's examples/MultiRobotExample.cpp
 // (which is hard-wired to 5 robots on torus3D), written against the public PGOAgent interface only.
 #include <DPGO/DPGO_utils.h>
+#include <DPGO/DeviceRBCD.h>
 #include <DPGO/PGOAgent.h>
 #include <DPGO/QuadraticProblem.h>
 
@@ -22,7 +27,9 @@ struct Options {
   std::string file, trace;
   unsigned robots = 5, iters = 1000, rank = 5;
   double stop = 0.1;
-  bool accel = false, rgd = false, jacobi = false;
+  bool accel = false, rgd = false, jacobi = false, resident = false;
+  unsigned gpus = 1, bench = 0;
+  std::string schedule = "greedy";
 };
 
 static Options parse(int argc, char **argv) {
@@ -38,6 +45,10 @@ static Options parse(int argc, char **argv) {
     else if (a == "--accel") o.accel = true;
     else if (a == "--rgd") o.rgd = true;
     else if (a == "--jacobi") o.jacobi = true;
+    else if (a == "--resident") o.resident = true;
+    else if (a == "--gpus") o.gpus = (unsigned)std::stoul(next());
+    else if (a == "--schedule") o.schedule = next();
+    else if (a == "--bench") o.bench = (unsigned)std::stoul(next());
     else if (a.rfind("--", 0) == 0) { std::cerr << "unknown option " << a << std::endl; std::exit(2); }
     else o.file = a;
   }
@@ -56,6 +67,43 @@ int main(int argc, char **argv) {
   if (graph.empty()) { std::cerr << "no measurements in " << opt.file << std::endl; return 1; }
   const unsigned d = (unsigned)graph[0].t.size(), r = opt.rank, K = opt.robots, dh = d + 1;
   if (n / K == 0) { std::cerr << "more robots than poses" << std::endl; return 1; }
+
+  if (opt.resident) {
+    // ---- device-resident runner: K agents over --gpus GPUs, one ncclAllGather per round ----
+    DeviceRBCDOptions ro;
+    ro.r = r;
+    ro.gpus = opt.gpus;
+    ro.schedule = opt.schedule;
+    ro.algorithm = opt.rgd ? ROPTALG::RGD : ROPTALG::RTR;
+    ro.preconditioner = opt.jacobi ? Preconditioner::BlockJacobi : Preconditioner::SparseExact;
+    const Matrix lifted0 = fixedStiefelVariable(d, r) * chordalInitialization(d, n, graph);
+    DeviceRBCD run(graph, n, K, lifted0, ro);
+    std::ofstream tr;
+    if (!opt.trace.empty()) tr.open(opt.trace);
+    const auto t0 = std::chrono::steady_clock::now();
+    unsigned it = 0;
+    DeviceRBCDStats st;
+    for (; it < opt.iters; ++it) {
+      st = run.step(true);
+      if (tr.is_open()) tr << std::setprecision(12) << it << "," << (st.active.empty() ? 0u : st.active[0]) << "," << st.cost << "," << st.gradnorm << "\n";
+      if (st.gradnorm < opt.stop) { ++it; break; }
+    }
+    const double sec = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    std::cout << std::setprecision(10) << "resident: agents = " << K << ", gpus = " << opt.gpus << ", schedule = " << opt.schedule << " ("
+              << run.numColours() << " colours), rounds = " << it << ", cost = " << st.cost << ", gradnorm = " << st.gradnorm
+              << ", seconds = " << sec << std::endl;
+    if (opt.bench > 0) {
+      run.runRounds(std::min(opt.bench, 20u));            // warm-up
+      run.sync();
+      const auto b0 = std::chrono::steady_clock::now();
+      run.runRounds(opt.bench);
+      run.sync();
+      const double bs = std::chrono::duration<double>(std::chrono::steady_clock::now() - b0).count();
+      std::cout << "bench: rounds = " << opt.bench << ", rounds/s = " << opt.bench / bs << ", us/round = " << 1e6 * bs / opt.bench
+                << ", all-gather bytes per GPU = " << run.allGatherBytesPerGpu() << std::endl;
+    }
+    return 0;
+  }
 
   // contiguous ownership: agent a owns [a * (n/K), (a+1) * (n/K)), the last agent takes the remainder
   const size_t per = n / K;

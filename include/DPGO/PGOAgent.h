@@ -56,6 +56,7 @@ struct PGOAgentParameters {
   bool logData;
   std::string logDirectory;
   Preconditioner preconditioner = Preconditioner::SparseExact;   // B200 extension
+  int device = -1;              // B200 extension: CUDA device of this agent's problem (-1: env DPGO_DEVICE or 0)
 
   PGOAgentParameters(unsigned dIn, unsigned rIn, unsigned numRobotsIn = 1, ROPTALG algorithmIn = ROPTALG::RTR,
                      bool accel = false, unsigned restartInt = 30, RobustCostType costType = RobustCostType::L2,
@@ -106,6 +107,7 @@ class PGOAgent {
   void initializeAcceleration();
 
   inline unsigned getID() const { return mID; }
+  inline QuadraticProblem *problem() const { return mProblemPtr; }   // B200 extension: the device-resident problem
   inline unsigned num_poses() const { return n; }
   inline unsigned dimension() const { return d; }
   inline unsigned relaxation_rank() const { return r; }

@@ -228,6 +228,15 @@ DPGO_API int dpgo_debug_phase_times32(dpgo_problem_t *p, int enable, double *ms_
 /* same with 64 slots: 32 + 3 k + {0, 1, 2} = gathers / panel jobs / epilogues of phase k (k < 10) as seen by CTA 0 */
 DPGO_API int dpgo_debug_phase_times64(dpgo_problem_t *p, int enable, double *ms_by_kind);
 
+/* ---- plain device helpers for hosts that drive several GPUs without linking the CUDA runtime themselves (the C++
+ *      multi-GPU runner: exchange buffers + one stream per GPU, NCCL calls on those streams) ---------------------- */
+DPGO_API int dpgo_device_set(int device);                                /* cudaSetDevice for the calling thread */
+DPGO_API int dpgo_device_malloc(int device, size_t bytes, void **ptr);   /* zero-initialised */
+DPGO_API int dpgo_device_free(int device, void *ptr);
+DPGO_API int dpgo_stream_create(int device, void **cuda_stream);
+DPGO_API int dpgo_stream_destroy(int device, void *cuda_stream);
+DPGO_API int dpgo_stream_synchronize(int device, void *cuda_stream);
+
 /* ---- boundary-pose exchange (multi-agent, one agent per GPU) ----------------------------- */
 /* ref: PGOAgent::getSharedPoseDict, src/PGOAgent.cpp:95-105: register which local poses are
  * public; pack gathers their r x (d+1) tiles into a contiguous device buffer (the NCCL

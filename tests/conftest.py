@@ -15,6 +15,15 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: test needs a CUDA device (run on the B200 box with -m gpu)")
 
 
+def pytest_collection_modifyitems(config, items):
+    """Tests marked gpu are skipped (not failed) on hosts without a CUDA device."""
+    if any("gpu" in item.keywords for item in items) and not has_gpu():
+        skip = pytest.mark.skip(reason="no CUDA device")
+        for item in items:
+            if "gpu" in item.keywords:
+                item.add_marker(skip)
+
+
 def has_gpu() -> bool:
     try:
         from dpo_b200 import _capi

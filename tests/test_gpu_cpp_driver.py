@@ -47,3 +47,32 @@ def test_cpp_driver_throughput_mode_converges(tmp_path):
     tr = run_driver(tmp_path, "smallGrid3D", "--robots", "4", "--iters", "600", "--stop", "0.1", "--jacobi")
     assert tr[-1, 3] < 0.1
     assert abs(tr[-1, 2] - 1025.398) <= 2e-4 * 1025.398
+
+
+def _device_count():
+    import ctypes
+    from dpo_b200 import _capi
+    c = ctypes.c_int(0)
+    _capi.load_library().dpgo_device_count(ctypes.byref(c))
+    return c.value
+
+
+@pytest.mark.parametrize("gpus", [1, 2])
+def test_cpp_resident_runner_reproduces_golden_trace(tmp_path, golden_dir, gpus):
+    """DPGO::DeviceRBCD (C++ host, iterates resident in HBM, public poses by ncclAllGather): greedy schedule, 5 agents
+    on 1 GPU -- and, where the box has them, coloured 8 agents over 2 GPUs against the oracle's coloured driver."""
+    if gpus > _device_count():
+        pytest.skip(f"needs {gpus} GPUs")
+    if gpus == 1:
+        tr = run_driver(tmp_path, "torus3D", "--robots", "5", "--iters", "40", "--stop", "0", "--resident")
+        gold = np.loadtxt(os.path.join(golden_dir, "NPtorus3D_head400.txt"), delimiter=",")[:40]
+        assert np.max(np.abs(tr[:, 2] - gold[:, 0]) / gold[:, 0]) <= 5e-9
+        assert np.max(np.abs(tr[:, 3] - gold[:, 1]) / gold[:, 1]) <= 5e-8
+    else:
+        tr = run_driver(tmp_path, "torus3D", "--robots", "8", "--iters", "10", "--stop", "0", "--resident", "--gpus", "2",
+                        "--schedule", "coloured")
+        meas, n = orc.read_g2o(os.path.join(ROOT, "data", "torus3D.g2o"))
+        drv = orc.MultiRobotDriver(meas, n, 8, r=5, schedule="coloured")
+        ot = drv.run(10)
+        assert np.max(np.abs(tr[:, 2] - np.array(ot.cost)) / np.array(ot.cost)) <= 1e-8
+        assert np.max(np.abs(tr[:, 3] - np.array(ot.gradnorm)) / np.array(ot.gradnorm)) <= 1e-7
