@@ -105,6 +105,13 @@ SIGNATURES = {
     "dpgo_agent_pack_public": (C.c_int, [_vp, _vp]),
     "dpgo_agent_set_shared_edges": (C.c_int, [_vp, C.c_int, _ip, _ip, _ip, _dp, _dp]),
     "dpgo_agent_build_G": (C.c_int, [_vp, _vp, C.c_int64]),
+    "dpgo_agent_accel_init": (C.c_int, [_vp]),
+    "dpgo_agent_accel_begin": (C.c_int, [_vp, C.c_double]),
+    "dpgo_agent_accel_end": (C.c_int, [_vp, C.c_double, C.c_int]),
+    "dpgo_agent_accel_restart_begin": (C.c_int, [_vp]),
+    "dpgo_agent_accel_restart_end": (C.c_int, [_vp]),
+    "dpgo_agent_pack_public_aux": (C.c_int, [_vp, _vp]),
+    "dpgo_optimize_resident_from_aux_async": (C.c_int, [_vp, C.POINTER(OptParams)]),
     "dpgo_agent_f_rgradnorm_resident": (C.c_int, [_vp, _dp, _dp]),
 }
 

@@ -155,6 +155,13 @@ class PGOAgent:
         self.readyToTerminate = False
         self.lastResult = None
         self.TLocalInit: Optional[np.ndarray] = None
+        # Nesterov acceleration (ref src/PGOAgent.cpp:1040-1091)
+        self.gamma = 0.0
+        self.alpha = 0.0
+        self.Y: Optional[np.ndarray] = None
+        self.V: Optional[np.ndarray] = None
+        self.XPrev: Optional[np.ndarray] = None
+        self.neighborAuxPoseDict: Dict[PoseID, np.ndarray] = {}
 
     # -- getters (ref .h:237-262) --
     def getID(self): return self.mID
@@ -267,6 +274,8 @@ class PGOAgent:
         assert Xin.shape == (self.r, (self.d + 1) * self.n)
         self.X = Xin.copy()
         self.mState = PGOAgentState.INITIALIZED
+        if self.mParams.acceleration:
+            self.initializeAcceleration()                  # ref :60-62
 
     def getX(self) -> np.ndarray:
         return self.X.copy()
@@ -290,13 +299,53 @@ class PGOAgent:
             if nid in self.neighborSharedPoseIDs and self.mState == PGOAgentState.INITIALIZED:
                 self.neighborPoseDict[nid] = np.array(var)
 
+    # -- Nesterov acceleration (ref src/PGOAgent.cpp:60-62, 107-118, 460-479, 1040-1091) --
+    def initializeAcceleration(self) -> None:
+        self.XPrev, self.V, self.Y = self.X.copy(), self.X.copy(), self.X.copy()
+        self.gamma = self.alpha = 0.0
+
+    def getAuxSharedPoseDict(self) -> Optional[Dict[PoseID, np.ndarray]]:
+        if self.mState != PGOAgentState.INITIALIZED or self.Y is None:
+            return None
+        dh = self.d + 1
+        return {pid: self.Y[:, pid[1] * dh:(pid[1] + 1) * dh].copy() for pid in self.localSharedPoseIDs}
+
+    def updateAuxNeighborPoses(self, neighborID: int, poseDict: Dict[PoseID, np.ndarray]) -> None:
+        assert neighborID != self.mID
+        for nid, var in poseDict.items():
+            if nid in self.neighborSharedPoseIDs and self.mState == PGOAgentState.INITIALIZED:
+                self.neighborAuxPoseDict[nid] = np.array(var)
+
     # -- one RBCD step (ref src/PGOAgent.cpp:642-718, updateX :1093-1165) --
     def iterate(self, doOptimization: bool = True) -> bool:
         self.mIterationNumber += 1
-        if self.mState != PGOAgentState.INITIALIZED or not doOptimization:
+        if self.mState != PGOAgentState.INITIALIZED:
+            return True
+        if not self.mParams.acceleration:
+            return self._updateX(doOptimization, False)
+        if self.Y is None:
+            self.initializeAcceleration()
+        self.XPrev = self.X.copy()
+        N = float(self.mParams.numRobots)
+        self.gamma = (1 + np.sqrt(1 + 4 * N * N * self.gamma * self.gamma)) / (2 * N)        # ref :1065-1069
+        self.alpha = 1.0 / (self.gamma * N)                                                    # ref :1071-1075
+        self.Y = self.mProblem.project((1 - self.alpha) * self.X + self.alpha * self.V)       # ref :1077-1083
+        ok = self._updateX(doOptimization, True)
+        self.V = self.mProblem.project(self.V + self.gamma * (self.X - self.Y))               # ref :1085-1091
+        if (self.mIterationNumber + 1) % self.mParams.restartInterval == 0:                    # ref :1033-1052
+            self.X = self.XPrev
+            self._updateX(doOptimization, False)
+            self.V, self.Y = self.X.copy(), self.X.copy()
+            self.gamma = self.alpha = 0.0
+        return ok
+
+    def _updateX(self, doOptimization: bool, acceleration: bool) -> bool:
+        if not doOptimization:
+            if acceleration:
+                self.X = self.Y.copy()
             return True
         XPrev = self.X
-        if not self.constructGMatrix(self.neighborPoseDict):
+        if not self.constructGMatrix(self.neighborAuxPoseDict if acceleration else self.neighborPoseDict):
             if self.mParams.verbose:
                 print(f"Robot {self.mID} could not construct G matrix. Skip update...")
             self.readyToTerminate = False
@@ -309,7 +358,7 @@ class PGOAgent:
         opt.setTrustRegionMaxInnerIterations(10)
         opt.setTrustRegionInitialRadius(100)
         opt.setPreconditioner(self.mParams.preconditioner)
-        self.X = np.array(opt.optimize(self.X))
+        self.X = np.array(opt.optimize(self.Y if acceleration else self.X))
         self.lastResult = opt.getOptResult()
         self.relativeChange = float(np.sqrt(np.sum((self.X - XPrev) ** 2) / self.n))
         self.readyToTerminate = self.relativeChange <= self.mParams.relChangeTol
@@ -386,8 +435,10 @@ class DistributedPGO:
     def __init__(self, edges: EdgeSet, n: int, k: int, r: int = 5, algorithm: int = ROPTALG.RTR,
                  preconditioner: int = capi.PRECOND_SPARSE_EXACT, schedule: str = "greedy",
                  owner: Optional[np.ndarray] = None, X_init: Optional[np.ndarray] = None,
-                 rank: Optional[int] = None, world: Optional[int] = None, device: int = 0, dist=None):
+                 rank: Optional[int] = None, world: Optional[int] = None, device: int = 0, dist=None,
+                 acceleration: bool = False, restart_interval: int = 30):
         import torch
+        self.acceleration, self.restart_interval = bool(acceleration), int(restart_interval)
         self.torch = torch
         self.dist = dist
         self.k, self.n, self.r, self.d = k, n, r, edges.d
@@ -443,6 +494,21 @@ class DistributedPGO:
         else:
             self.send_all = None
             self.send = {a: self.gathered[a * self.slot_elems:(a + 1) * self.slot_elems] for a in self.local_ids}
+        if self.acceleration:
+            # Nesterov-accelerated RBCD (ref src/PGOAgent.cpp:685-695,1040-1091): auxiliary iterates resident per agent,
+            # their public tiles in a second gathered buffer (ref getAuxSharedPoseDict / updateAuxNeighborPoses)
+            self.gathered_aux = torch.zeros_like(self.gathered)
+            if self.distributed:
+                self.send_aux_all = torch.zeros_like(self.send_all)
+                base = self.local_ids[0]
+                self.send_aux = {a: self.send_aux_all[(a - base) * self.slot_elems:(a - base + 1) * self.slot_elems]
+                                 for a in self.local_ids}
+            else:
+                self.send_aux_all = None
+                self.send_aux = {a: self.gathered_aux[a * self.slot_elems:(a + 1) * self.slot_elems] for a in self.local_ids}
+            self.acc = {a: dict(gamma=0.0, alpha=0.0, it=0) for a in self.local_ids}
+            for a in self.local_ids:
+                capi.check(self.agents[a].mProblem._lib.dpgo_agent_accel_init(self.agents[a].mProblem._h))
         self.stats_local = torch.zeros(4 * len(self.local_ids), dtype=torch.float64, device=self.dev)
         self.stats_all = torch.zeros(4 * k, dtype=torch.float64, device=self.dev)
         self.selected = [0]
@@ -481,8 +547,71 @@ class DistributedPGO:
         gn2 = vals[:, 2]
         return cost, float(np.sqrt(np.sum(gn2))), np.sqrt(gn2)
 
+    def _step_accelerated(self) -> List[int]:
+        """One round of the accelerated schedule, every update on the device.  Order as in the reference's driver
+        (examples/MultiRobotExample.cpp:236-279): every agent advances gamma / alpha / Y; the idle agents finish their
+        iterate(false) (X = Y, V, restart); public tiles of X and of Y are exchanged; the active agents step from Y
+        with G built from the neighbours' auxiliary poses."""
+        active = self._active()
+        N = float(self.k)
+        lib = self.agents[self.local_ids[0]].mProblem._lib
+
+        def restart_due(a):
+            return (self.acc[a]["it"] + 1) % self.restart_interval == 0
+
+        def finish_restart(a):
+            capi.check(lib.dpgo_agent_accel_restart_end(self.agents[a].mProblem._h))
+            self.acc[a]["gamma"] = self.acc[a]["alpha"] = 0.0
+
+        for a in self.local_ids:
+            st, h = self.acc[a], self.agents[a].mProblem._h
+            st["it"] += 1
+            st["gamma"] = (1 + np.sqrt(1 + 4 * N * N * st["gamma"] ** 2)) / (2 * N)
+            st["alpha"] = 1.0 / (st["gamma"] * N)
+            capi.check(lib.dpgo_agent_accel_begin(h, st["alpha"]))
+            if a not in active:
+                capi.check(lib.dpgo_agent_accel_end(h, st["gamma"], 0))
+                if restart_due(a):                         # ref :1040-1052 with doOptimization == false: X = XPrev
+                    capi.check(lib.dpgo_agent_accel_restart_begin(h))
+                    finish_restart(a)
+        # exchange X tiles and Y tiles
+        for a in self.local_ids:
+            self.agents[a].pack_public(self.send[a].data_ptr())
+            capi.check(lib.dpgo_agent_pack_public_aux(self.agents[a].mProblem._h, C.c_void_p(self.send_aux[a].data_ptr())))
+        if self.distributed:
+            self.dist.all_gather_into_tensor(self.gathered, self.send_all)
+            self.dist.all_gather_into_tensor(self.gathered_aux, self.send_aux_all)
+        for a in self.local_ids:
+            if a not in active:
+                continue
+            ag, st = self.agents[a], self.acc[a]
+            h = ag.mProblem._h
+            ag.build_G(self.gathered_aux.data_ptr(), self.k * self.plan.pmax)
+            capi.check(lib.dpgo_optimize_resident_from_aux_async(h, C.byref(ag.opt.params())))
+            capi.check(lib.dpgo_agent_accel_end(h, st["gamma"], 1))
+            if restart_due(a):                             # X = XPrev, one plain step on the neighbours' X, V = Y = X
+                capi.check(lib.dpgo_agent_accel_restart_begin(h))
+                ag.build_G(self.gathered.data_ptr(), self.k * self.plan.pmax)
+                ag.opt.optimize_resident_async()
+                finish_restart(a)
+        for a in self.local_ids:
+            if a in active:
+                self.agents[a].lastResult = self.agents[a].opt.fetch_result()
+                self.agents[a].mIterationNumber += 1
+        return active
+
     def step(self, evaluate: bool = True) -> Optional[RoundStats]:
         """One round: exchange, active agents optimise, (optionally) exchange again + evaluate + select."""
+        if self.acceleration:
+            active = self._step_accelerated()
+            self.round += 1
+            if not evaluate:
+                return None
+            self.exchange()
+            cost, gn, per_agent = self.evaluate()
+            if self.schedule == "greedy" and self.plan.tables[self.selected[0]]["neighbors"]:
+                self.selected = [int(np.argmax(per_agent))]
+            return RoundStats(cost, gn, active)
         self.exchange()
         active = self._active()
         for a in self.local_ids:

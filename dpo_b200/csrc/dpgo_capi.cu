@@ -74,6 +74,7 @@ struct dpgo_problem {
   int64_t nd_info[16] = {};
   // vectors
   double *d_G = nullptr;
+  double *d_acc[3] = {nullptr, nullptr, nullptr};   // Nesterov acceleration: Y, V, XPrev (allocated by accel_init)
   double *d_vec[dpgo::V_COUNT] = {};
   double *d_S[2] = {nullptr, nullptr};
   double *d_partials = nullptr;
@@ -642,6 +643,7 @@ int dpgo_problem_destroy(dpgo_problem_t *p) {
   free_dev(p->d_dense_t2); free_dev(p->d_ppack); free_dev(p->d_sym_off); free_dev(p->d_sym_cut); free_dev(p->d_sym_segptr); free_dev(p->d_sym_cfirst); free_dev(p->d_sym_ccount);
   for (int i = 0; i < dpgo::V_COUNT; ++i) free_dev(p->d_vec[i]);
   free_dev(p->d_S[0]); free_dev(p->d_S[1]); free_dev(p->d_partials); free_dev(p->d_bar); free_dev(p->d_phase_ns); free_dev(p->d_result);
+  free_dev(p->d_acc[0]); free_dev(p->d_acc[1]); free_dev(p->d_acc[2]);
   free_dev(p->d_public); free_dev(p->d_pose_ids); free_dev(p->d_pose_ptr); free_dev(p->d_edge_slot);
   free_dev(p->d_edge_out); free_dev(p->d_edge_T); free_dev(p->d_edge_om);
   free_nd(p);
@@ -1253,6 +1255,59 @@ int dpgo_agent_build_G(dpgo_problem_t *p, const double *gathered_dev, int64_t nu
     DPGO_CUDA(dpgo::launch_build_G(p->r, p->dh, p->num_shared_poses, p->d_pose_ids, p->d_pose_ptr, p->d_edge_slot,
                                    p->d_edge_out, p->d_edge_T, p->d_edge_om, gathered_dev, p->d_G, p->stream));
   return DPGO_OK;
+}
+
+// ---- Nesterov acceleration on the resident iterate ----------------------------------------------------
+#define DPGO_ACC_READY(p) DPGO_REQUIRE((p)->d_acc[0], DPGO_ERR_STATE, "dpgo_agent_accel_init has not been called")
+int dpgo_agent_accel_init(dpgo_problem_t *p) {
+  DPGO_CHECK_HANDLE(p);
+  for (int i = 0; i < 3; ++i) {
+    if (!p->d_acc[i]) DPGO_CUDA(cudaMalloc(&p->d_acc[i], p->vec_bytes()));
+    DPGO_CUDA(cudaMemcpyAsync(p->d_acc[i], p->d_vec[dpgo::V_X0], p->vec_bytes(), cudaMemcpyDeviceToDevice, p->stream));
+  }
+  return DPGO_OK;
+}
+int dpgo_agent_accel_begin(dpgo_problem_t *p, double alpha) {
+  DPGO_CHECK_HANDLE(p);
+  DPGO_ACC_READY(p);
+  double *X = p->d_vec[dpgo::V_X0], *Y = p->d_acc[0], *V = p->d_acc[1], *XP = p->d_acc[2];
+  DPGO_CUDA(cudaMemcpyAsync(XP, X, p->vec_bytes(), cudaMemcpyDeviceToDevice, p->stream));
+  DPGO_CUDA(dpgo::launch_stiefel_project(p->r, p->dh, p->n, X, Y, p->stream, 1.0 - alpha, V, alpha));
+  return DPGO_OK;
+}
+int dpgo_agent_accel_end(dpgo_problem_t *p, double gamma, int optimized) {
+  DPGO_CHECK_HANDLE(p);
+  DPGO_ACC_READY(p);
+  double *X = p->d_vec[dpgo::V_X0], *Y = p->d_acc[0], *V = p->d_acc[1];
+  if (!optimized) DPGO_CUDA(cudaMemcpyAsync(X, Y, p->vec_bytes(), cudaMemcpyDeviceToDevice, p->stream));
+  DPGO_CUDA(dpgo::launch_stiefel_project(p->r, p->dh, p->n, V, V, p->stream, 1.0, X, gamma, Y, -gamma));
+  return DPGO_OK;
+}
+int dpgo_agent_accel_restart_begin(dpgo_problem_t *p) {
+  DPGO_CHECK_HANDLE(p);
+  DPGO_ACC_READY(p);
+  DPGO_CUDA(cudaMemcpyAsync(p->d_vec[dpgo::V_X0], p->d_acc[2], p->vec_bytes(), cudaMemcpyDeviceToDevice, p->stream));
+  return DPGO_OK;
+}
+int dpgo_agent_accel_restart_end(dpgo_problem_t *p) {
+  DPGO_CHECK_HANDLE(p);
+  DPGO_ACC_READY(p);
+  for (int i = 0; i < 2; ++i)
+    DPGO_CUDA(cudaMemcpyAsync(p->d_acc[i], p->d_vec[dpgo::V_X0], p->vec_bytes(), cudaMemcpyDeviceToDevice, p->stream));
+  return DPGO_OK;
+}
+int dpgo_agent_pack_public_aux(dpgo_problem_t *p, double *send_dev) {
+  DPGO_CHECK_HANDLE(p);
+  DPGO_ACC_READY(p);
+  DPGO_REQUIRE(send_dev || p->num_public == 0, DPGO_ERR_INVALID_ARG, "null send buffer");
+  DPGO_CUDA(dpgo::launch_pack_tiles(p->ts, p->num_public, p->d_public, p->d_acc[0], send_dev, p->stream));
+  return DPGO_OK;
+}
+int dpgo_optimize_resident_from_aux_async(dpgo_problem_t *p, const dpgo_opt_params_t *params) {
+  DPGO_CHECK_HANDLE(p);
+  DPGO_ACC_READY(p);
+  DPGO_CUDA(cudaMemcpyAsync(p->d_vec[dpgo::V_X0], p->d_acc[0], p->vec_bytes(), cudaMemcpyDeviceToDevice, p->stream));
+  return dpgo_optimize_resident_async(p, params);
 }
 
 int dpgo_agent_f_rgradnorm_resident(dpgo_problem_t *p, double *f_out, double *norm_out) {

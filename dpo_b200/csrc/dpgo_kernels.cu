@@ -1284,17 +1284,27 @@ __global__ void __launch_bounds__(SPMV_THREADS) k_spmv(int n, const int *__restr
 // the r x d block -- columns are rotated until mutually orthogonal (Y V = U Sigma), which keeps high
 // relative accuracy for ill-conditioned blocks -- then out = U V^T.
 // ---------------------------------------------------------------------------------------------
-template <int R, int DH> __global__ void k_stiefel_project(int n, const double *__restrict__ M, double *__restrict__ out) {
+// The input is the linear combination c0 A + c1 B + c2 C (B, C optional): the Nesterov updates of the accelerated RBCD,
+// Y = proj((1 - alpha) X + alpha V) and V = proj(V + gamma (X - Y)) (ref src/PGOAgent.cpp:1077-1091), are one launch each.
+// (M and out may be the same buffer: a thread reads its whole tile before it writes it -- hence no __restrict__.)
+template <int R, int DH> __global__ void k_stiefel_project(int n, const double *M, double *out, double c0, const double *B, double c1,
+                                                            const double *Cc, double c2) {
   constexpr int D = DH - 1;
   constexpr int TS = R * DH;
   const int j = blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= n) return;
+  auto in = [&](int e) {
+    double v = c0 * M[(size_t)j * TS + e];
+    if (B) v = fma(c1, B[(size_t)j * TS + e], v);
+    if (Cc) v = fma(c2, Cc[(size_t)j * TS + e], v);
+    return v;
+  };
   double y[D][R];
   double V[D][D];
 #pragma unroll
   for (int c = 0; c < D; ++c) {
 #pragma unroll
-    for (int a = 0; a < R; ++a) y[c][a] = M[(size_t)j * TS + c * R + a];
+    for (int a = 0; a < R; ++a) y[c][a] = in(c * R + a);
 #pragma unroll
     for (int q = 0; q < D; ++q) V[c][q] = (c == q) ? 1.0 : 0.0;     // V[c] = column c of V
   }
@@ -1352,7 +1362,7 @@ template <int R, int DH> __global__ void k_stiefel_project(int n, const double *
       out[(size_t)j * TS + c * R + a] = s;
     }
 #pragma unroll
-  for (int a = 0; a < R; ++a) out[(size_t)j * TS + D * R + a] = M[(size_t)j * TS + D * R + a];
+  for (int a = 0; a < R; ++a) out[(size_t)j * TS + D * R + a] = in(D * R + a);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1498,10 +1508,11 @@ cudaError_t launch_spmv(int r, int dh, int n, const int *rowptr, const int *bcol
   return cudaGetLastError();
 }
 
-cudaError_t launch_stiefel_project(int r, int dh, int n, const double *M, double *out, cudaStream_t stream) {
+cudaError_t launch_stiefel_project(int r, int dh, int n, const double *M, double *out, cudaStream_t stream, double c0,
+                                   const double *B, double c1, const double *C, double c2) {
   bool ok = false;
   DPGO_DISPATCH(r, dh, {
-    k_stiefel_project<R, DH><<<(n + 127) / 128, 128, 0, stream>>>(n, M, out);
+    k_stiefel_project<R, DH><<<(n + 127) / 128, 128, 0, stream>>>(n, M, out, c0, B, c1, C, c2);
     ok = true;
   });
   if (!ok) return cudaErrorInvalidValue;

@@ -99,7 +99,8 @@ cudaError_t launch_spmv_tma(int r, int dh, int ngroups, const int2 *groups, cons
                             const double *bval, const double *X, const double *G, double *out, int sms,
                             cudaStream_t stream);
 int optimize_max_grid(int r, int dh, int device);   // co-resident CTA count for the persistent kernel
-cudaError_t launch_stiefel_project(int r, int dh, int n, const double *M, double *out, cudaStream_t stream);
+cudaError_t launch_stiefel_project(int r, int dh, int n, const double *M, double *out, cudaStream_t stream, double c0 = 1.0,
+                                   const double *B = nullptr, double c1 = 0.0, const double *C = nullptr, double c2 = 0.0);
 cudaError_t launch_pack_tiles(int ts, int count, const int *pose, const double *X, double *out, cudaStream_t stream);
 cudaError_t launch_build_G(int r, int dh, int nposes, const int *pose_ids, const int *pose_ptr, const int *edge_slot,
                            const int *edge_out, const double *edge_T, const double *edge_om, const double *gathered,

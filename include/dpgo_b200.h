@@ -252,6 +252,19 @@ DPGO_API int dpgo_agent_set_shared_edges(dpgo_problem_t *p, int num_edges, const
                                 const double *omega);
 /* rebuild G in HBM from the gathered neighbour tiles (deterministic: edges grouped per pose) */
 DPGO_API int dpgo_agent_build_G(dpgo_problem_t *p, const double *gathered_dev, int64_t num_slots);
+/* ---- Nesterov-accelerated RBCD on the resident iterate (ref src/PGOAgent.cpp:685-695 iterate, :1040-1091 updateGamma /
+ *      updateAlpha / updateY / updateV / restart; the scalars gamma, alpha stay with the host, which follows the reference's
+ *      recurrences).  All calls are asynchronous on the handle's stream. */
+DPGO_API int dpgo_agent_accel_init(dpgo_problem_t *p);                     /* V = Y = XPrev = X        (ref :60-62, :1040-1052) */
+DPGO_API int dpgo_agent_accel_begin(dpgo_problem_t *p, double alpha);       /* XPrev = X; Y = proj((1 - alpha) X + alpha V)  (ref :1077-1083) */
+/* optimized == 0: X = Y (ref updateX(false, true), :1095-1098); then V = proj(V + gamma (X - Y))  (ref :1085-1091) */
+DPGO_API int dpgo_agent_accel_end(dpgo_problem_t *p, double gamma, int optimized);
+DPGO_API int dpgo_agent_accel_restart_begin(dpgo_problem_t *p);             /* X = XPrev  (then the caller takes a plain step) */
+DPGO_API int dpgo_agent_accel_restart_end(dpgo_problem_t *p);               /* V = Y = X */
+/* public tiles of the auxiliary iterate Y (ref getAuxSharedPoseDict, :107-118) */
+DPGO_API int dpgo_agent_pack_public_aux(dpgo_problem_t *p, double *send_dev);
+/* X = Y, then optimise X in place (ref updateX(true, true): the step starts from the auxiliary iterate) */
+DPGO_API int dpgo_optimize_resident_from_aux_async(dpgo_problem_t *p, const dpgo_opt_params_t *params);
 /* per-agent Riemannian gradient norm / cost of the resident iterate (greedy selection input) */
 DPGO_API int dpgo_agent_f_rgradnorm_resident(dpgo_problem_t *p, double *f_out, double *norm_out);
 

@@ -90,6 +90,82 @@ def test_host_level_round_equals_resident_round(data_dir):
         assert np.linalg.norm(Xh - X0) <= tol * np.linalg.norm(X0)
 
 
+def test_accelerated_rbcd_on_the_device_matches_oracle(data_dir):
+    """Nesterov-accelerated RBCD (ref src/PGOAgent.cpp:685-695,1040-1091) with every update on the device -- gamma / alpha
+    recurrences on the host, Y and V by the fused combination + Stiefel projection kernel, auxiliary public poses in a
+    second gathered buffer, restart every 30 iterations -- against the oracle's accelerated greedy driver."""
+    from dpo_b200.agent import DistributedPGO
+    edges, n = load("smallGrid3D", data_dir)
+    meas, _ = orc.read_g2o(os.path.join(data_dir, "smallGrid3D.g2o"))
+    iters = 70                                           # two restarts (iterations 29 and 59)
+    run = DistributedPGO(edges, n, 5, r=5, schedule="greedy", acceleration=True)
+    drv = orc.MultiRobotDriver(meas, n, 5, r=5, acceleration=True)
+    sel = []
+    for it in range(iters):
+        st = run.step()
+        cost, gn = drv.step()
+        sel.append(st.selected[0])
+        assert abs(st.cost - cost) <= 1e-8 * abs(cost), it
+        assert abs(st.gradnorm - gn) <= 1e-6 * gn, it
+    assert sel == drv.trace.selected
+    assert np.linalg.norm(run.assemble() - drv.assemble()) <= 1e-8 * np.linalg.norm(drv.assemble())
+
+
+def test_accelerated_coloured_schedule_converges(data_dir):
+    """All agents of a colour class step from their auxiliary iterates every round (the concurrent accelerated schedule):
+    monotone up to the restarts' safeguards, reaches the optimum of smallGrid3D (f* = 1025.4, vis.ipynb:108745)."""
+    from dpo_b200.agent import DistributedPGO
+    edges, n = load("smallGrid3D", data_dir)
+    run = DistributedPGO(edges, n, 5, r=5, schedule="coloured", acceleration=True)
+    last = None
+    for it in range(300):
+        last = run.step(evaluate=(it % 10 == 9))
+        if last is not None and last.gradnorm < 0.05:
+            break
+    assert last is not None and last.gradnorm < 0.1
+    assert abs(last.cost - 1025.398) <= 2e-4 * 1025.398
+
+
+def test_python_host_agent_acceleration_matches_oracle(data_dir):
+    """The Python PGOAgent mirror with acceleration = True through the reference's PoseDict protocol
+    (examples/MultiRobotExample.cpp:236-279) against the oracle."""
+    from dpo_b200.agent import PGOAgent, PGOAgentParameters, contiguous_owner, partition_edges
+    from dpo_b200 import posegraph as pg
+    edges, n = load("smallGrid3D", data_dir)
+    meas, _ = orc.read_g2o(os.path.join(data_dir, "smallGrid3D.g2o"))
+    k, r, d = 4, 5, edges.d
+    dh = d + 1
+    parts, counts, glob = partition_edges(edges, contiguous_owner(n, k), k)
+    X0 = pg.fixedStiefelVariable(d, r) @ pg.chordalInitialization(d, n, edges)
+    agents = []
+    for a in range(k):
+        ag = PGOAgent(a, PGOAgentParameters(d, r, k, acceleration=True))
+        ag.YLift = None
+        ag.setPoseGraph(*parts[a], TInit=np.zeros((d, dh * int(counts[a]))), n=int(counts[a]))
+        cols = (glob[a][:, None] * dh + np.arange(dh)[None, :]).ravel()
+        ag.setX(X0[:, cols])
+        agents.append(ag)
+    drv = orc.MultiRobotDriver(meas, n, k, r=r, acceleration=True)
+    selected = 0
+    for it in range(35):                                  # crosses the restart at iteration 29
+        sel = agents[selected]
+        for ag in agents:
+            if ag.mID != selected:
+                ag.iterate(False)
+        for ag in agents:
+            if ag.mID != selected:
+                sel.updateNeighborPoses(ag.mID, ag.getSharedPoseDict())
+                sel.updateAuxNeighborPoses(ag.mID, ag.getAuxSharedPoseDict())
+        sel.iterate(True)
+        drv.step()
+        X = np.zeros_like(X0)
+        for a, ag in enumerate(agents):
+            cols = (glob[a][:, None] * dh + np.arange(dh)[None, :]).ravel()
+            X[:, cols] = ag.X
+        assert np.linalg.norm(X - drv.assemble()) <= 1e-8 * np.linalg.norm(X), it
+        selected = drv.selected                           # follow the oracle's greedy choice
+
+
 def test_device_G_matches_host_G(data_dir):
     """dpgo_agent_build_G (device, from gathered slots) == constructGMatrix (host dictionary form)."""
     from dpo_b200.agent import DistributedPGO
