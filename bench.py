@@ -477,6 +477,16 @@ def run_gpu_arm(args):
                 line["multi_agent_1gpu"][ds] = {k2: m[k2] for k2 in ("rounds_per_sec", "ms_per_round", "agent_steps_per_sec", "colours", "final")}
         if not args.no_spmv:
             line["roofline_spmv"] = spmv_roofline(torch, dp, pg, peak, peak_src)
+            if not args.no_sweep:
+                # SURVEY 8(d) / BASELINE.md section 4: the sweep across the L2 boundary (10k ... 1M poses at 4 edges / pose)
+                sweep = []
+                for dims in ((25, 20, 20), (40, 30, 25), (50, 50, 40), (100, 60, 50), (100, 100, 100)):
+                    rr = spmv_roofline(torch, dp, pg, peak, peak_src, dims=dims, reps=20)
+                    sweep.append({"poses": dims[0] * dims[1] * dims[2], "algorithmic_bytes_per_launch": rr["algorithmic_bytes_per_launch"],
+                                  "us_per_launch": rr["us_per_launch"], "achieved": rr["achieved"], "frac": rr["frac"]})
+                line["roofline_spmv"]["sweep"] = sweep
+                line["roofline_spmv"]["sweep_note"] = ("same kernel, inputs from L2-resident (10k-30k poses: 15-45 MB) to far beyond L2 "
+                                                       "(1M poses: 1.5 GB); back-to-back launches, so the small sizes are served by L2")
         # ---- CPU restatement of the reference path on the host cores, bounded sample ----
         if not args.no_cpu:
             _, _, info = cpu_reference_steps(2 * CYCLE, 1)
@@ -632,6 +642,7 @@ def main():
     ap.add_argument("--no-spmv", action="store_true", help="skip the synthetic SpMV roofline leg")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-multi", action="store_true", help="N = 1: skip the 8-agents-on-one-GPU leg")
+    ap.add_argument("--no-sweep", action="store_true", help="N = 1: skip the SpMV size sweep")
     ap.add_argument("--precond", default="sparse", choices=["sparse", "dense"],
                     help="exact preconditioner implementation: nested-dissection block solve (default) or the dense inverse (A/B)")
     args = ap.parse_args()

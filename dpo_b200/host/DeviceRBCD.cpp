@@ -30,7 +30,8 @@ struct DeviceRBCD::Impl {
   size_t n = 0;
   std::string schedule;
   std::vector<std::unique_ptr<PGOAgent>> agents;
-  std::vector<size_t> first, count;
+  std::vector<size_t> count;
+  std::vector<std::vector<size_t>> globalOf;      // agent -> global pose ids in local order
   std::vector<dpgo_problem *> h;
   std::vector<int> gpuOf;
   std::vector<void *> stream;
@@ -64,16 +65,18 @@ DeviceRBCD::DeviceRBCD(const std::vector<RelativeSEMeasurement> &graph, size_t n
   I.perGpu = I.K / I.N;
   const unsigned K = I.K, d = I.d, dh = I.dh, r = I.r;
 
-  // ---- contiguous ownership (ref examples/MultiRobotExample.cpp:95-151) ----
+  // ---- ownership: partition file or contiguous ranges (ref examples/MultiRobotExample.cpp:76-151) ----
   const size_t per = n / K;
   std::vector<unsigned> owner(n), local(n);
+  if (!opt.owner.empty() && opt.owner.size() != n) throw std::runtime_error("DeviceRBCD: owner map must have one entry per pose");
   I.count.assign(K, 0);
   for (size_t g = 0; g < n; ++g) {
-    owner[g] = (unsigned)std::min<size_t>(g / per, K - 1);
+    owner[g] = opt.owner.empty() ? (unsigned)std::min<size_t>(g / per, K - 1) : opt.owner[g];
+    if (owner[g] >= K) throw std::runtime_error("DeviceRBCD: agent id out of range in the owner map");
     local[g] = (unsigned)I.count[owner[g]]++;
   }
-  I.first.assign(K, 0);
-  for (unsigned a = 1; a < K; ++a) I.first[a] = I.first[a - 1] + I.count[a - 1];
+  I.globalOf.assign(K, {});
+  for (size_t g = 0; g < n; ++g) I.globalOf[owner[g]].push_back(g);
   std::vector<std::vector<RelativeSEMeasurement>> odo(K), priv(K), shared(K);
   for (const auto &e : graph) {
     const unsigned a1 = owner[e.p1], a2 = owner[e.p2];
@@ -101,7 +104,9 @@ DeviceRBCD::DeviceRBCD(const std::vector<RelativeSEMeasurement> &graph, size_t n
     else I.agents[a]->setLiftingMatrix(lift);
     // a zero trajectory of the right shape skips the agent's own chordal initialisation: X comes from XInit
     I.agents[a]->setPoseGraph(odo[a], priv[a], shared[a], Matrix::Zero(d, dh * I.count[a]));
-    I.agents[a]->setX(Matrix(XInit).block(0, I.first[a] * dh, r, I.count[a] * dh));
+    Matrix Xa0(r, dh * I.count[a]);
+    for (size_t q = 0; q < I.count[a]; ++q) Xa0.block(0, q * dh, r, dh) = Matrix(XInit).block(0, I.globalOf[a][q] * dh, r, dh);
+    I.agents[a]->setX(Xa0);
     I.h[a] = I.agents[a]->problem()->handle();
     if (!I.h[a]) throw std::runtime_error("DeviceRBCD: agent without a device problem");
     check(dpgo_problem_set_stream(I.h[a], I.stream[(size_t)I.gpuOf[a]]), "dpgo_problem_set_stream");
@@ -287,7 +292,7 @@ Matrix DeviceRBCD::assemble() {
   for (unsigned a = 0; a < I.K; ++a) {
     Matrix Xa(I.r, I.dh * I.count[a]);
     check(dpgo_problem_download_X(I.h[a], Xa.data()), "dpgo_problem_download_X");
-    X.block(0, I.first[a] * I.dh, I.r, I.count[a] * I.dh) = Xa;
+    for (size_t q = 0; q < I.count[a]; ++q) X.block(0, I.globalOf[a][q] * I.dh, I.r, I.dh) = Xa.block(0, q * I.dh, I.r, I.dh);
   }
   return X;
 }

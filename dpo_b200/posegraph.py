@@ -351,3 +351,15 @@ def synthetic_grid_graph(nx: int, ny: int, nz: int, edges_per_pose: float = 4.0,
     Tgt.reshape(3, n, 4)[:, :, :3] = np.transpose(Rgt, (1, 0, 2))
     Tgt.reshape(3, n, 4)[:, :, 3] = tgt.T
     return edges, n, Tgt
+
+
+def read_partition_file(path: str, n: int | None = None) -> np.ndarray:
+    """Pose -> agent map from a graph-partition file, one agent id per line in pose order
+    (ref examples/MultiRobotExample.cpp:76-91: graph/<robots>/<strength>/<dataset>)."""
+    owner = np.loadtxt(path, dtype=np.int64, ndmin=1)
+    if n is not None and owner.shape[0] != n:
+        raise ValueError(f"partition file has {owner.shape[0]} lines, the pose graph has {n} poses")
+    if owner.min() < 0:
+        raise ValueError("negative agent id in the partition file")
+    return owner
+

@@ -1,7 +1,8 @@
 // MultiAgentPGO -- command-line driver of the B200 distributed pose-graph optimiser (C++ host API).
 //
 //   MultiAgentPGO <file.g2o> [--robots K] [--iters N] [--stop GRADNORM] [--accel] [--rgd] [--jacobi]
-//                 [--rank R] [--trace out.csv] [--resident [--gpus N] [--schedule greedy|coloured|parallel] [--bench ROUNDS]]
+//                 [--rank R] [--trace out.csv] [--resident [--gpus N] [--schedule greedy|coloured|parallel] [--bench ROUNDS]
+//                                                           [--partition FILE]]
 //
 // --resident runs the device-resident multi-GPU runner (DPGO::DeviceRBCD): iterates stay in HBM, K agents over N GPUs
 // of this node, ONE ncclAllGather of the public poses per round; --bench times ROUNDS rounds without the central
@@ -29,7 +30,7 @@ struct Options {
   double stop = 0.1;
   bool accel = false, rgd = false, jacobi = false, resident = false;
   unsigned gpus = 1, bench = 0;
-  std::string schedule = "greedy";
+  std::string schedule = "greedy", partition;
 };
 
 static Options parse(int argc, char **argv) {
@@ -49,6 +50,7 @@ static Options parse(int argc, char **argv) {
     else if (a == "--gpus") o.gpus = (unsigned)std::stoul(next());
     else if (a == "--schedule") o.schedule = next();
     else if (a == "--bench") o.bench = (unsigned)std::stoul(next());
+    else if (a == "--partition") o.partition = next();
     else if (a.rfind("--", 0) == 0) { std::cerr << "unknown option " << a << std::endl; std::exit(2); }
     else o.file = a;
   }
@@ -76,6 +78,13 @@ int main(int argc, char **argv) {
     ro.schedule = opt.schedule;
     ro.algorithm = opt.rgd ? ROPTALG::RGD : ROPTALG::RTR;
     ro.preconditioner = opt.jacobi ? Preconditioner::BlockJacobi : Preconditioner::SparseExact;
+    if (!opt.partition.empty()) {                        // one agent id per line, pose order (ref examples/MultiRobotExample.cpp:76-91)
+      std::ifstream pf(opt.partition);
+      std::string line;
+      while (std::getline(pf, line))
+        if (!line.empty()) ro.owner.push_back((unsigned)std::stoul(line));
+      if (ro.owner.size() != n) { std::cerr << "partition file: " << ro.owner.size() << " lines for " << n << " poses" << std::endl; return 1; }
+    }
     const Matrix lifted0 = fixedStiefelVariable(d, r) * chordalInitialization(d, n, graph);
     DeviceRBCD run(graph, n, K, lifted0, ro);
     std::ofstream tr;

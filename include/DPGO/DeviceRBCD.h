@@ -32,6 +32,9 @@ struct DeviceRBCDOptions {
   std::string schedule = "greedy";
   ROPTALG algorithm = ROPTALG::RTR;
   Preconditioner preconditioner = Preconditioner::SparseExact;
+  // pose -> agent (one entry per pose, e.g. from a graph-partition file, ref examples/MultiRobotExample.cpp:76-91);
+  // empty: contiguous ranges, the last agent takes the remainder (ref :95-109)
+  std::vector<unsigned> owner;
 };
 
 struct DeviceRBCDStats {

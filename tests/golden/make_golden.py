@@ -16,6 +16,9 @@ DATASETS = ["CSAIL", "grid3D", "parking-garage", "smallGrid3D", "sphere2500", "t
 LINES = 400
 # final rounded trajectories X[:, :d]^T X the reference ships (result/opt_pose/NP<dataset>.csv, d x (d+1)n), copied whole
 OPT_POSE = ["parking-garage"]
+# graph-partition runs (examples/MultiRobotExample.cpp:76-91 reads graph/<robots>/<strength>/<dataset>, one agent id per line;
+# the matching trace is result/graph/<strength><dataset>.txt): (strength, dataset) pairs carried as fixtures
+PARTITIONED = [("strong", "CSAIL"), ("strong", "smallGrid3D"), ("strong", "sphere2500")]
 
 
 def main():
@@ -49,6 +52,21 @@ def main():
             with open(dst, "w") as fh:
                 fh.write(body)
             print(f"wrote {dst}")
+    for strength, ds in PARTITIONED:
+        pairs = [(os.path.join(args.reference, "graph", "5", strength, ds), os.path.join(HERE, f"partition5_{strength}_{ds}.txt"), None),
+                 (os.path.join(args.reference, "result", "graph", f"{strength}{ds}.txt"),
+                  os.path.join(HERE, f"{strength}{ds}_head400.txt"), LINES)]
+        for src, dst, lines in pairs:
+            with open(src) as fh:
+                body = "".join(fh.readlines()[:lines]) if lines else fh.read()
+            if args.check:
+                same = os.path.exists(dst) and open(dst).read() == body
+                print(f"{os.path.basename(dst)}: {'identical' if same else 'DIFFERS'}")
+                bad += 0 if same else 1
+            else:
+                with open(dst, "w") as fh:
+                    fh.write(body)
+                print(f"wrote {dst}")
     sys.exit(1 if bad else 0)
 
 

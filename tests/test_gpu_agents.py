@@ -34,6 +34,25 @@ def test_greedy_schedule_reproduces_golden_trace(ds, iters, data_dir, golden_dir
     assert np.max(np.abs(np.array(gn) - gold[:, 1]) / gold[:, 1]) <= gtol
 
 
+@pytest.mark.parametrize("ds,iters", [("CSAIL", 60), ("sphere2500", 40)])
+def test_partition_file_reproduces_golden_trace(ds, iters, data_dir, golden_dir):
+    """Non-contiguous ownership from the reference's partition files (graph/5/strong/<dataset>) through the device
+    runner: agents own scattered poses, public poses are most of them -- against result/graph/strong<dataset>.txt."""
+    from dpo_b200.agent import DistributedPGO
+    from dpo_b200 import posegraph as pg
+    edges, n = load(ds, data_dir)
+    owner = pg.read_partition_file(os.path.join(golden_dir, f"partition5_strong_{ds}.txt"), n)
+    run = DistributedPGO(edges, n, 5, r=5, schedule="greedy", owner=owner)
+    gold = np.loadtxt(os.path.join(golden_dir, f"strong{ds}_head400.txt"), delimiter=",")[:iters]
+    cost, gn = [], []
+    for _ in range(iters):
+        st = run.step()
+        cost.append(st.cost)
+        gn.append(st.gradnorm)
+    assert np.max(np.abs(np.array(cost) - gold[:, 0]) / gold[:, 0]) <= 5e-9
+    assert np.max(np.abs(np.array(gn) - gold[:, 1]) / gold[:, 1]) <= 5e-8
+
+
 @pytest.mark.parametrize("ds,k,rounds", [("torus3D", 8, 10), ("parking-garage", 4, 8), ("sphere2500", 8, 8)])
 def test_coloured_schedule_matches_oracle(ds, k, rounds, data_dir):
     """The schedule the multi-GPU benchmark runs (BASELINE configs 3 and 4 and the sphere2500 scaling workload): k

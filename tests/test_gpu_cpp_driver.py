@@ -76,3 +76,12 @@ def test_cpp_resident_runner_reproduces_golden_trace(tmp_path, golden_dir, gpus)
         ot = drv.run(10)
         assert np.max(np.abs(tr[:, 2] - np.array(ot.cost)) / np.array(ot.cost)) <= 1e-8
         assert np.max(np.abs(tr[:, 3] - np.array(ot.gradnorm)) / np.array(ot.gradnorm)) <= 1e-7
+
+
+def test_cpp_resident_runner_with_partition_file(tmp_path, golden_dir):
+    """--partition: ownership from the reference's graph-partition file through the C++ resident runner."""
+    tr = run_driver(tmp_path, "CSAIL", "--robots", "5", "--iters", "50", "--stop", "0", "--resident", "--partition",
+                    os.path.join(golden_dir, "partition5_strong_CSAIL.txt"))
+    gold = np.loadtxt(os.path.join(golden_dir, "strongCSAIL_head400.txt"), delimiter=",")[:50]
+    assert np.max(np.abs(tr[:, 2] - gold[:, 0]) / gold[:, 0]) <= 5e-9
+    assert np.max(np.abs(tr[:, 3] - gold[:, 1]) / gold[:, 1]) <= 5e-8

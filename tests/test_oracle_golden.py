@@ -82,6 +82,19 @@ def test_coloured_schedule_is_sequential_rbcd(data_dir):
     assert all(np.diff(a.trace.cost) <= 1e-9)
 
 
+@pytest.mark.parametrize("ds,iters", [("CSAIL", 60), ("smallGrid3D", 60), ("sphere2500", 30)])
+def test_partition_file_traces(ds, iters, data_dir, golden_dir):
+    """Graph-partition runs (ref examples/MultiRobotExample.cpp:76-91): agent ids from graph/5/strong/<dataset>, trace
+    result/graph/strong<dataset>.txt (partition ingestion)."""
+    meas, n = load(ds, data_dir)
+    owner = np.loadtxt(os.path.join(golden_dir, f"partition5_strong_{ds}.txt"), dtype=np.int64)
+    drv = orc.MultiRobotDriver(meas, n, 5, r=5, owner=owner)
+    tr = drv.run(iters)
+    gold = np.loadtxt(os.path.join(golden_dir, f"strong{ds}_head400.txt"), delimiter=",")[:iters]
+    assert np.max(np.abs(np.array(tr.cost) - gold[:, 0]) / gold[:, 0]) <= 5e-9
+    assert np.max(np.abs(np.array(tr.gradnorm) - gold[:, 1]) / gold[:, 1]) <= 5e-9
+
+
 def test_single_robot_known_answers(data_dir):
     """SingleRobotExample Cost = 18.51936666 (3 outer / 29 inner) on tinyGrid3D."""
     cost, res, _ = orc.single_robot_example(os.path.join(data_dir, "tinyGrid3D.g2o"))
