@@ -5,6 +5,8 @@
 #include <DPGO/DPGO_robust.h>
 #include <DPGO/DPGO_utils.h>
 
+#include "dpgo_b200.h"
+
 #include <cmath>
 #include <fstream>
 #include <sstream>
@@ -301,6 +303,30 @@ Matrix odometryInitialization(size_t dimension, size_t num_poses, const std::vec
     T.block(0, (src + 1) * dh, d, d) = R;
     T.block(0, (src + 1) * dh + d, d, 1) = t;
   }
+  return T;
+}
+
+Matrix chordalInitializationGPU(size_t dimension, size_t num_poses, const std::vector<RelativeSEMeasurement> &measurements,
+                                int device, double tol) {
+  const size_t d = dimension, m = measurements.size();
+  std::vector<int32_t> p1(m), p2(m);
+  std::vector<double> R(m * d * d), t(m * d), kappa(m), tau(m);
+  for (size_t e = 0; e < m; ++e) {
+    const RelativeSEMeasurement &ms = measurements[e];
+    p1[e] = (int32_t)ms.p1;
+    p2[e] = (int32_t)ms.p2;
+    for (size_t a = 0; a < d; ++a) {
+      for (size_t b = 0; b < d; ++b) R[e * d * d + a * d + b] = ms.R(a, b);
+      t[e * d + a] = ms.t(a);
+    }
+    kappa[e] = ms.weight * ms.kappa;
+    tau[e] = ms.weight * ms.tau;
+  }
+  if (device < 0) { const char *ev = std::getenv("DPGO_DEVICE"); device = ev ? std::atoi(ev) : 0; }
+  Matrix T((Eigen::Index)d, (Eigen::Index)((d + 1) * num_poses));
+  if (dpgo_chordal_initialization((int)num_poses, (int)d, (int64_t)m, p1.data(), p2.data(), R.data(), t.data(), kappa.data(), tau.data(),
+                                  device, tol, 0, T.data(), nullptr) != DPGO_OK)
+    throw std::runtime_error(std::string("dpgo_chordal_initialization: ") + dpgo_chordal_last_error());
   return T;
 }
 

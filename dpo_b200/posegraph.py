@@ -275,6 +275,28 @@ def chordalInitialization(d: int, n: int, edges: EdgeSet) -> np.ndarray:
     return T
 
 
+def chordalInitializationGPU(d: int, n: int, edges: EdgeSet, device: int = 0, tol: float = 1e-11, max_iter: int = 50000,
+                             return_iterations: bool = False):
+    """chordalInitialization on the GPU (dpgo_chordal_initialization): both least-squares problems by Jacobi-preconditioned
+    conjugate gradients over the hot path's block-CSR product kernel.  ref src/DPGO_utils.cpp:273-461."""
+    import ctypes as C
+    from . import _capi as capi
+    lib = capi.load_library()
+    p1 = np.ascontiguousarray(edges.p1, dtype=np.int32)
+    p2 = np.ascontiguousarray(edges.p2, dtype=np.int32)
+    R = np.ascontiguousarray(edges.R, dtype=np.float64)
+    t = np.ascontiguousarray(edges.t, dtype=np.float64)
+    kappa = np.ascontiguousarray(edges.kappa * edges.weight, dtype=np.float64)
+    tau = np.ascontiguousarray(edges.tau * edges.weight, dtype=np.float64)
+    T = np.zeros((d, (d + 1) * n), order="F")
+    its = (C.c_int32 * 2)()
+    code = lib.dpgo_chordal_initialization(n, d, len(p1), capi.iptr(p1), capi.iptr(p2), capi.dptr(R), capi.dptr(t), capi.dptr(kappa),
+                                           capi.dptr(tau), device, tol, max_iter, capi.dptr(T), its)
+    if code != capi.OK:
+        raise capi.DpgoError(code, lib.dpgo_chordal_last_error().decode("utf-8", "replace"))
+    return (T, (int(its[0]), int(its[1]))) if return_iterations else T
+
+
 def synthetic_grid_graph(nx: int, ny: int, nz: int, edges_per_pose: float = 4.0, seed: int = 0,
                          rot_sigma: float = 0.05, trans_sigma: float = 0.1, kappa: float = 200.0,
                          tau: float = 100.0) -> Tuple[EdgeSet, int, np.ndarray]:

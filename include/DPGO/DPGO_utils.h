@@ -22,6 +22,10 @@ SparseMatrix constructConnectionLaplacianSE(const std::vector<RelativeSEMeasurem
 
 // initial guesses; ref src/DPGO_utils.cpp:362-461
 Matrix chordalInitialization(size_t dimension, size_t num_poses, const std::vector<RelativeSEMeasurement> &measurements);
+// B200 extension: the same two least-squares problems solved on the GPU (conjugate gradients over the block-CSR product
+// kernel, dpgo_chordal_initialization); device < 0: env DPGO_DEVICE or 0.  Throws std::runtime_error on failure.
+Matrix chordalInitializationGPU(size_t dimension, size_t num_poses, const std::vector<RelativeSEMeasurement> &measurements,
+                                int device = -1, double tol = 1e-11);
 Matrix odometryInitialization(size_t dimension, size_t num_poses, const std::vector<RelativeSEMeasurement> &odometry);
 
 // projections; ref src/DPGO_utils.cpp:463-492

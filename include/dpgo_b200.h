@@ -228,6 +228,18 @@ DPGO_API int dpgo_debug_phase_times32(dpgo_problem_t *p, int enable, double *ms_
 /* same with 64 slots: 32 + 3 k + {0, 1, 2} = gathers / panel jobs / epilogues of phase k (k < 10) as seen by CTA 0 */
 DPGO_API int dpgo_debug_phase_times64(dpgo_problem_t *p, int enable, double *ms_by_kind);
 
+/* ---- chordal initialisation on the GPU ------------------------------------------------------------------------
+ * ref: chordalInitialization, src/DPGO_utils.cpp:273-461 (two sparse least-squares problems, SPQR there; gauge R_0 = I,
+ * t_0 = 0) + projectToRotationGroup :463-477.  Both normal systems are 3 x 3-block connection Laplacians, solved by
+ * Jacobi-preconditioned conjugate gradients whose product is the TMA-fed block-CSR kernel of the hot path.
+ * m edges p1 -> p2 (pose ids), R: m x d x d row-major, t: m x d, kappa / tau: m.  T_host: d x (d+1)n column-major
+ * ([R_p t_p] per pose, the layout of the reference's Matrix).  tol: relative residual (<= 0: 1e-11); iterations2[2]
+ * (nullable) receives the CG iteration counts of the two solves.  dpgo_chordal_last_error() for the message. */
+DPGO_API int dpgo_chordal_initialization(int n, int d, int64_t m, const int32_t *p1, const int32_t *p2, const double *R,
+                                         const double *t, const double *kappa, const double *tau, int device, double tol,
+                                         int max_iter, double *T_host, int32_t *iterations2);
+DPGO_API const char *dpgo_chordal_last_error(void);
+
 /* ---- plain device helpers for hosts that drive several GPUs without linking the CUDA runtime themselves (the C++
  *      multi-GPU runner: exchange buffers + one stream per GPU, NCCL calls on those streams) ---------------------- */
 DPGO_API int dpgo_device_set(int device);                                /* cudaSetDevice for the calling thread */
