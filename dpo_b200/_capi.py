@@ -61,6 +61,9 @@ SIGNATURES = {
                                     C.POINTER(C.c_int64)]),
     "dpgo_problem_set_Q_csr": (C.c_int, [_vp, C.c_int, _ip, _ip, _dp, C.c_uint]),
     "dpgo_problem_set_Q_blocks": (C.c_int, [_vp, C.c_int64, _ip, _ip, _dp, C.c_uint]),
+    "dpgo_problem_set_edges": (C.c_int, [_vp, C.c_int64, _ip, _ip, _dp, _dp, _dp, _dp, _dp, _ip, C.c_int64, _ip, _dp, C.c_uint]),
+    "dpgo_problem_robust_reweight": (C.c_int, [_vp, C.c_int, C.c_double, C.c_double, _dp, _dp]),
+    "dpgo_problem_set_edge_weights": (C.c_int, [_vp, _dp]),
     "dpgo_problem_set_G_dense": (C.c_int, [_vp, _dp]),
     "dpgo_problem_set_G_csr": (C.c_int, [_vp, _ip, _ip, _dp]),
     "dpgo_problem_f": (C.c_int, [_vp, _dp, _dp]),

@@ -231,8 +231,8 @@ class PGOAgent:
     def constructQMatrix(self) -> None:
         """Private edges' Laplacian + diagonal terms of the shared edges (ref src/PGOAgent.cpp:720-781)."""
         priv = EdgeSet.join([self.odometry, self.privateLoopClosures])
-        brow, bcol, blocks = pg.connection_laplacian_blocks(priv)
         sh = self.sharedLoopClosures
+        idx, W = None, None
         if len(sh):
             T, om = sh.homogeneous(), sh.omega()
             out = sh.r1 == self.mID
@@ -242,10 +242,10 @@ class PGOAgent:
             Wout = (T * om[:, None, :]) @ np.transpose(T, (0, 2, 1))       # outgoing: T Omega T^T at p1
             W[out] = Wout[out]
             idx = np.where(out, sh.p1, sh.p2).astype(np.int32)
-            brow = np.concatenate([brow, idx])
-            bcol = np.concatenate([bcol, idx])
-            blocks = np.concatenate([blocks, W], axis=0)
-        self.mProblem.setQ_blocks(brow, bcol, blocks)
+        # the private edges' Laplacian is assembled on the device from the edge records (k_assemble_Q); the shared edges'
+        # diagonal terms enter as static blocks; odometry edges keep their weights under robust re-weighting
+        fixed = np.concatenate([np.ones(len(self.odometry), dtype=np.int32), np.zeros(len(self.privateLoopClosures), dtype=np.int32)])
+        self.mProblem.setEdges(priv, idx, W, fixed=fixed)
 
     def constructGMatrix(self, poseDict: Dict[PoseID, np.ndarray]) -> bool:
         """Host form (dictionary of neighbour poses), as the reference does it (src/PGOAgent.cpp:783-859)."""

@@ -72,6 +72,11 @@ struct dpgo_problem {
   dpgo::KNd nd = {};
   dpgo::nd::Hierarchy *nd_H = nullptr;
   int64_t nd_info[16] = {};
+  // edge records for the device-side Q assembly / robust re-weighting (dpgo_problem_set_edges)
+  int64_t ne = 0;
+  int *d_e_p1 = nullptr, *d_e_p2 = nullptr, *d_e_fixed = nullptr, *d_cptr = nullptr;
+  int2 *d_contrib = nullptr;
+  double *d_eT = nullptr, *d_eom = nullptr, *d_ew = nullptr, *d_sblk = nullptr, *d_eres = nullptr;
   // vectors
   double *d_G = nullptr;
   double *d_acc[3] = {nullptr, nullptr, nullptr};   // Nesterov acceleration: Y, V, XPrev (allocated by accel_init)
@@ -414,6 +419,34 @@ void assemble_bsr(int n, const std::vector<BlockTriplet> &trip, std::vector<int>
   for (int j = 0; j < n; ++j) rowptr[j + 1] += rowptr[j];
 }
 
+// block-Jacobi inverse blocks (Q_jj + 0.1 I)^-1, stored [k][c] padded
+void jacobi_blocks(int n, int dh, const std::vector<int> &rowptr, const std::vector<int> &bcol, const std::vector<double> &bval,
+                   std::vector<double> &dinv) {
+  dinv.assign((size_t)n * 16, 0.0);
+  for (int j = 0; j < n; ++j) {
+    double A[4][8];
+    for (int k = 0; k < 4; ++k)
+      for (int c = 0; c < 8; ++c) A[k][c] = (c >= 4 && c - 4 == k) ? 1.0 : 0.0;
+    for (int k = 0; k < dh; ++k) A[k][k] = 0.1;
+    for (int k = dh; k < 4; ++k) A[k][k] = 1.0;
+    for (int b = rowptr[j]; b < rowptr[j + 1]; ++b)
+      if (bcol[b] == j)
+        for (int k = 0; k < dh; ++k)
+          for (int c = 0; c < dh; ++c) A[k][c] += bval[(size_t)b * 16 + k * 4 + c];
+    for (int k = 0; k < 4; ++k) {          // Gauss-Jordan, SPD so no pivoting
+      const double inv = 1.0 / A[k][k];
+      for (int c = 0; c < 8; ++c) A[k][c] *= inv;
+      for (int i = 0; i < 4; ++i)
+        if (i != k) {
+          const double f = A[i][k];
+          for (int c = 0; c < 8; ++c) A[i][c] -= f * A[k][c];
+        }
+    }
+    for (int k = 0; k < dh; ++k)
+      for (int c = 0; c < dh; ++c) dinv[(size_t)j * 16 + k * 4 + c] = A[k][4 + c];
+  }
+}
+
 int build_from_triplets(dpgo_problem *p, std::vector<BlockTriplet> &trip, unsigned precond_mask) {
   const int n = p->n, dh = p->dh;
   std::vector<int> rowptr, bcol;
@@ -421,33 +454,8 @@ int build_from_triplets(dpgo_problem *p, std::vector<BlockTriplet> &trip, unsign
   assemble_bsr(n, trip, rowptr, bcol, bval);
   const int64_t nb = (int64_t)bcol.size();
 
-  // block-Jacobi inverse blocks (Q_jj + 0.1 I)^-1, stored [k][c] padded
   std::vector<double> dinv;
-  if (precond_mask & (1u << DPGO_PRECOND_BLOCK_JACOBI)) {
-    dinv.assign((size_t)n * 16, 0.0);
-    for (int j = 0; j < n; ++j) {
-      double A[4][8];
-      for (int k = 0; k < 4; ++k)
-        for (int c = 0; c < 8; ++c) A[k][c] = (c >= 4 && c - 4 == k) ? 1.0 : 0.0;
-      for (int k = 0; k < dh; ++k) A[k][k] = 0.1;
-      for (int k = dh; k < 4; ++k) A[k][k] = 1.0;
-      for (int b = rowptr[j]; b < rowptr[j + 1]; ++b)
-        if (bcol[b] == j)
-          for (int k = 0; k < dh; ++k)
-            for (int c = 0; c < dh; ++c) A[k][c] += bval[(size_t)b * 16 + k * 4 + c];
-      for (int k = 0; k < 4; ++k) {          // Gauss-Jordan, SPD so no pivoting
-        const double inv = 1.0 / A[k][k];
-        for (int c = 0; c < 8; ++c) A[k][c] *= inv;
-        for (int i = 0; i < 4; ++i)
-          if (i != k) {
-            const double f = A[i][k];
-            for (int c = 0; c < 8; ++c) A[i][c] -= f * A[k][c];
-          }
-      }
-      for (int k = 0; k < dh; ++k)
-        for (int c = 0; c < dh; ++c) dinv[(size_t)j * 16 + k * 4 + c] = A[k][4 + c];
-    }
-  }
+  if (precond_mask & (1u << DPGO_PRECOND_BLOCK_JACOBI)) jacobi_blocks(n, dh, rowptr, bcol, bval, dinv);
 
   // persistent-kernel grid and balanced row partition
   const int sg = (p->r > 4) ? 32 : ((p->r > 2) ? 16 : 8);
@@ -644,6 +652,8 @@ int dpgo_problem_destroy(dpgo_problem_t *p) {
   for (int i = 0; i < dpgo::V_COUNT; ++i) free_dev(p->d_vec[i]);
   free_dev(p->d_S[0]); free_dev(p->d_S[1]); free_dev(p->d_partials); free_dev(p->d_bar); free_dev(p->d_phase_ns); free_dev(p->d_result);
   free_dev(p->d_acc[0]); free_dev(p->d_acc[1]); free_dev(p->d_acc[2]);
+  free_dev(p->d_e_p1); free_dev(p->d_e_p2); free_dev(p->d_e_fixed); free_dev(p->d_cptr); free_dev(p->d_contrib);
+  free_dev(p->d_eT); free_dev(p->d_eom); free_dev(p->d_ew); free_dev(p->d_sblk); free_dev(p->d_eres);
   free_dev(p->d_public); free_dev(p->d_pose_ids); free_dev(p->d_pose_ptr); free_dev(p->d_edge_slot);
   free_dev(p->d_edge_out); free_dev(p->d_edge_T); free_dev(p->d_edge_om);
   free_nd(p);
@@ -1134,6 +1144,124 @@ int dpgo_nd_debug_emulate(int n, int d, int r, int64_t nb, const int32_t *brow, 
     return fail(DPGO_ERR_UNSUPPORTED, std::string("sparse exact preconditioner: ") + e.what());
   }
   return DPGO_OK;
+}
+
+// ---- Q from edge records on the device, robust re-weighting -----------------------------------------------------
+static int reassemble_Q(dpgo_problem *p) {
+  DPGO_CUDA(dpgo::launch_assemble_Q(p->nb, p->d_cptr, p->d_contrib, p->d_eT, p->d_eom, p->d_ew, p->d_sblk, p->d_bval, p->stream));
+  // the host copy feeds the lazily built exact preconditioners; block-Jacobi blocks are refreshed right away
+  DPGO_CUDA(cudaMemcpyAsync(p->h_bval.data(), p->d_bval, sizeof(double) * 16 * (size_t)p->nb, cudaMemcpyDeviceToHost, p->stream));
+  DPGO_CUDA(cudaStreamSynchronize(p->stream));
+  if (p->d_dinv) {
+    std::vector<double> dinv;
+    jacobi_blocks(p->n, p->dh, p->h_rowptr, p->h_bcol, p->h_bval, dinv);
+    DPGO_CUDA(cudaMemcpyAsync(p->d_dinv, dinv.data(), sizeof(double) * dinv.size(), cudaMemcpyHostToDevice, p->stream));
+    DPGO_CUDA(cudaStreamSynchronize(p->stream));
+  }
+  free_nd(p);                                            // (Q + 0.1 I)^-1 changed: rebuilt on next use
+  free_dev(p->d_pinv); free_dev(p->d_dense_part); free_dev(p->d_dense_t2); free_dev(p->d_ppack); free_dev(p->d_sym_off);
+  free_dev(p->d_sym_cut); free_dev(p->d_sym_segptr); free_dev(p->d_sym_cfirst); free_dev(p->d_sym_ccount);
+  p->sym_ok = 0;
+  return DPGO_OK;
+}
+
+int dpgo_problem_set_edges(dpgo_problem_t *p, int64_t m, const int32_t *p1, const int32_t *p2, const double *R, const double *t,
+                           const double *kappa, const double *tau, const double *weight, const int32_t *fixed_weight,
+                           int64_t num_static, const int32_t *static_pose, const double *static_blocks, unsigned precond_mask) {
+  DPGO_CHECK_HANDLE(p);
+  DPGO_REQUIRE(m >= 0 && (m == 0 || (p1 && p2 && R && t && kappa && tau)), DPGO_ERR_INVALID_ARG, "null edge arrays");
+  DPGO_REQUIRE(num_static >= 0 && (num_static == 0 || (static_pose && static_blocks)), DPGO_ERR_INVALID_ARG, "null static blocks");
+  const int d = p->d, dh = p->dh, n = p->n;
+  for (int64_t e = 0; e < m; ++e)
+    if (p1[e] < 0 || p1[e] >= n || p2[e] < 0 || p2[e] >= n) return fail(DPGO_ERR_INVALID_ARG, "edge endpoint out of range");
+  for (int64_t q = 0; q < num_static; ++q)
+    if (static_pose[q] < 0 || static_pose[q] >= n) return fail(DPGO_ERR_INVALID_ARG, "static block pose out of range");
+  // pattern: zero-valued triplets give the block-CSR structure (and the usual launch tables) ...
+  std::vector<BlockTriplet> trip;
+  trip.reserve((size_t)(4 * m + num_static));
+  auto add = [&](int bi, int bj) { BlockTriplet bt; bt.brow = bi; bt.bcol = bj; std::memset(bt.v, 0, sizeof(bt.v)); trip.push_back(bt); };
+  for (int64_t e = 0; e < m; ++e) { add(p1[e], p1[e]); add(p2[e], p2[e]); add(p1[e], p2[e]); add(p2[e], p1[e]); }
+  for (int64_t q = 0; q < num_static; ++q) add(static_pose[q], static_pose[q]);
+  DPGO_TRY(build_from_triplets(p, trip, precond_mask));
+  // ... and every block's contribution list in input order: block (bi, bj) = entry with bcol == bi in row bj
+  const std::vector<int> &rowptr = p->h_rowptr, &bcol = p->h_bcol;
+  auto find_block = [&](int bi, int bj) {
+    const int *lo = bcol.data() + rowptr[(size_t)bj], *hi = bcol.data() + rowptr[(size_t)bj + 1];
+    return (int)(std::lower_bound(lo, hi, bi) - bcol.data());
+  };
+  const int64_t nb = p->nb;
+  std::vector<int> cnt((size_t)nb + 1, 0);
+  std::vector<std::pair<int, int2>> items;             // (block, (index, kind))
+  items.reserve((size_t)(4 * m + num_static));
+  for (int64_t e = 0; e < m; ++e) {
+    items.push_back({find_block(p1[e], p1[e]), make_int2((int)e, 0)});
+    items.push_back({find_block(p2[e], p2[e]), make_int2((int)e, 1)});
+    items.push_back({find_block(p1[e], p2[e]), make_int2((int)e, 2)});
+    items.push_back({find_block(p2[e], p1[e]), make_int2((int)e, 3)});
+  }
+  for (int64_t q = 0; q < num_static; ++q) items.push_back({find_block(static_pose[q], static_pose[q]), make_int2((int)q, 4)});
+  for (auto &it : items) cnt[(size_t)it.first + 1]++;
+  for (int64_t b = 0; b < nb; ++b) cnt[(size_t)b + 1] += cnt[(size_t)b];
+  std::vector<int2> contrib(items.size());
+  {
+    std::vector<int> fill(cnt.begin(), cnt.end() - 1);
+    for (auto &it : items) contrib[(size_t)fill[(size_t)it.first]++] = it.second;     // input order inside a block
+  }
+  std::vector<double> eT((size_t)m * 16, 0.0), eom((size_t)m * 4, 0.0), ew((size_t)m, 1.0), sb((size_t)num_static * 16, 0.0);
+  std::vector<int> fx((size_t)m, 0), q1((size_t)m), q2((size_t)m);
+  for (int64_t e = 0; e < m; ++e) {
+    double *T = &eT[(size_t)e * 16];
+    for (int a = 0; a < d; ++a) {
+      for (int b = 0; b < d; ++b) T[a * 4 + b] = R[(size_t)e * d * d + a * d + b];
+      T[a * 4 + d] = t[(size_t)e * d + a];
+      eom[(size_t)e * 4 + a] = kappa[e];
+    }
+    T[d * 4 + d] = 1.0;
+    eom[(size_t)e * 4 + d] = tau[e];
+    if (weight) ew[(size_t)e] = weight[e];
+    if (fixed_weight) fx[(size_t)e] = fixed_weight[e] ? 1 : 0;
+    q1[(size_t)e] = p1[e];
+    q2[(size_t)e] = p2[e];
+  }
+  for (int64_t q = 0; q < num_static; ++q)
+    for (int a = 0; a < dh; ++a)
+      for (int b = 0; b < dh; ++b) sb[(size_t)q * 16 + a * 4 + b] = static_blocks[(size_t)q * dh * dh + a * dh + b];
+  free_dev(p->d_e_p1); free_dev(p->d_e_p2); free_dev(p->d_e_fixed); free_dev(p->d_cptr); free_dev(p->d_contrib);
+  free_dev(p->d_eT); free_dev(p->d_eom); free_dev(p->d_ew); free_dev(p->d_sblk); free_dev(p->d_eres);
+  p->ne = m;
+  auto up = [&](auto *&dst, const auto &src) -> cudaError_t {
+    using T = typename std::remove_reference<decltype(src[0])>::type;
+    cudaError_t e = cudaMalloc(&dst, sizeof(T) * std::max<size_t>(src.size(), 1));
+    if (e == cudaSuccess && !src.empty()) e = cudaMemcpy(dst, src.data(), sizeof(T) * src.size(), cudaMemcpyHostToDevice);
+    return e;
+  };
+  DPGO_CUDA(up(p->d_e_p1, q1)); DPGO_CUDA(up(p->d_e_p2, q2)); DPGO_CUDA(up(p->d_e_fixed, fx)); DPGO_CUDA(up(p->d_cptr, cnt));
+  DPGO_CUDA(up(p->d_contrib, contrib)); DPGO_CUDA(up(p->d_eT, eT)); DPGO_CUDA(up(p->d_eom, eom)); DPGO_CUDA(up(p->d_ew, ew));
+  DPGO_CUDA(up(p->d_sblk, sb));
+  DPGO_CUDA(cudaMalloc(&p->d_eres, sizeof(double) * std::max<int64_t>(m, 1)));
+  return reassemble_Q(p);
+}
+
+int dpgo_problem_set_edge_weights(dpgo_problem_t *p, const double *weights_host) {
+  DPGO_CHECK_HANDLE(p);
+  DPGO_REQUIRE(p->d_cptr, DPGO_ERR_STATE, "dpgo_problem_set_edges has not been called");
+  DPGO_REQUIRE(weights_host || p->ne == 0, DPGO_ERR_INVALID_ARG, "null weights");
+  if (p->ne) DPGO_CUDA(cudaMemcpyAsync(p->d_ew, weights_host, sizeof(double) * (size_t)p->ne, cudaMemcpyHostToDevice, p->stream));
+  return reassemble_Q(p);
+}
+
+int dpgo_problem_robust_reweight(dpgo_problem_t *p, int cost, double mu, double param, double *weights_host, double *residuals2_host) {
+  DPGO_CHECK_HANDLE(p);
+  DPGO_REQUIRE(p->d_cptr, DPGO_ERR_STATE, "dpgo_problem_set_edges has not been called");
+  DPGO_REQUIRE(cost >= 0 && cost <= 5, DPGO_ERR_INVALID_ARG, "unknown robust cost");
+  DPGO_REQUIRE(cost != 5 || mu > 0, DPGO_ERR_INVALID_ARG, "GNC needs mu > 0");
+  DPGO_CUDA(dpgo::launch_edge_weights(p->r, p->dh, p->ne, p->d_e_p1, p->d_e_p2, p->d_eT, p->d_eom, p->d_e_fixed, p->d_vec[dpgo::V_X0], cost,
+                                      mu, param, p->d_ew, p->d_eres, p->stream));
+  if (weights_host && p->ne)
+    DPGO_CUDA(cudaMemcpyAsync(weights_host, p->d_ew, sizeof(double) * (size_t)p->ne, cudaMemcpyDeviceToHost, p->stream));
+  if (residuals2_host && p->ne)
+    DPGO_CUDA(cudaMemcpyAsync(residuals2_host, p->d_eres, sizeof(double) * (size_t)p->ne, cudaMemcpyDeviceToHost, p->stream));
+  return reassemble_Q(p);
 }
 
 // ---- plain device helpers ----------------------------------------------------------------------

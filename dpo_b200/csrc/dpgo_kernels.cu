@@ -1409,6 +1409,83 @@ __global__ void k_build_G(int nposes, const int *__restrict__ pose_ids, const in
 }
 
 // ---------------------------------------------------------------------------------------------
+// Q from edge records on the device (ref: constructConnectionLaplacianSE, src/DPGO_utils.cpp:199-271, and the diagonal terms
+// of PGOAgent::constructQMatrix, src/PGOAgent.cpp:720-781): one thread per block entry walks the block's contribution
+// list in input order (deterministic).  Per edge i -> j with T = [R t; 0 1], Om = w diag(kappa.., tau):
+//   kind 0  Q_ii += T Om T^T     kind 1  Q_jj += Om     kind 2  Q_ij = -T Om     kind 3  Q_ji = -Om T^T     kind 4  static block
+// ---------------------------------------------------------------------------------------------
+__global__ void k_assemble_Q(int64_t nb, const int *__restrict__ cptr, const int2 *__restrict__ contrib, const double *__restrict__ eT,
+                             const double *__restrict__ eom, const double *__restrict__ ew, const double *__restrict__ sblk,
+                             double *__restrict__ bval) {
+  const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (tid >= nb * 16) return;
+  const int64_t b = tid >> 4;
+  const int k = (int)((tid >> 2) & 3), c = (int)(tid & 3);
+  double v = 0.0;
+  for (int q = cptr[b]; q < cptr[b + 1]; ++q) {
+    const int2 cc = contrib[q];
+    if (cc.y == 4) { v += sblk[(size_t)cc.x * 16 + k * 4 + c]; continue; }
+    const double *T = eT + (size_t)cc.x * 16, *om = eom + (size_t)cc.x * 4;
+    const double w = ew[cc.x];
+    if (cc.y == 0) {
+      double s = 0.0;
+#pragma unroll
+      for (int u = 0; u < 4; ++u) s = fma(T[k * 4 + u] * (om[u] * w), T[c * 4 + u], s);
+      v += s;
+    } else if (cc.y == 1) {
+      if (k == c) v += om[k] * w;
+    } else if (cc.y == 2) {
+      v -= T[k * 4 + c] * (om[c] * w);
+    } else {
+      v -= (om[k] * w) * T[c * 4 + k];
+    }
+  }
+  bval[tid] = v;
+}
+
+// Robust re-weighting (ref: PGOAgent::updateLoopClosuresWeights, src/PGOAgent.cpp:1181-1245; computeMeasurementError,
+// src/DPGO_utils.cpp:494-500; RobustCost::weight, src/DPGO_robust.cpp:23-66): one thread per private edge evaluates
+// r^2 = kappa |Y_i R - Y_j|^2 + tau |p_j - p_i - Y_i t|^2 at the resident iterate and the weight of the chosen loss.
+// cost: 0 L2, 1 L1, 2 Huber(param), 3 TLS(param), 4 Geman-McClure, 5 GNC_TLS(mu, param = cbar)
+template <int R, int DH>
+__global__ void k_edge_weights(int64_t m, const int *__restrict__ p1, const int *__restrict__ p2, const double *__restrict__ eT,
+                               const double *__restrict__ eom, const int *__restrict__ fixed, const double *__restrict__ X, int cost,
+                               double mu, double param, double *__restrict__ w, double *__restrict__ resid) {
+  constexpr int D = DH - 1, TS = R * DH;
+  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= m) return;
+  const double *T = eT + (size_t)e * 16, *om = eom + (size_t)e * 4;
+  const double *X1 = X + (size_t)p1[e] * TS, *X2 = X + (size_t)p2[e] * TS;
+  double rot = 0.0, tra = 0.0;
+  for (int a = 0; a < R; ++a) {
+    for (int c = 0; c < D; ++c) {
+      double s = -X2[c * R + a];
+      for (int q = 0; q < D; ++q) s = fma(X1[q * R + a], T[q * 4 + c], s);
+      rot = fma(s, s, rot);
+    }
+    double s = X2[D * R + a] - X1[D * R + a];
+    for (int q = 0; q < D; ++q) s = fma(-X1[q * R + a], T[q * 4 + D], s);
+    tra = fma(s, s, tra);
+  }
+  const double r2 = om[0] * rot + om[D] * tra;
+  if (resid) resid[e] = r2;
+  if (fixed && fixed[e]) return;
+  const double r = sqrt(r2);
+  double wt = 1.0;
+  if (cost == 1) wt = 1.0 / r;
+  else if (cost == 2) wt = (r < param) ? 1.0 : param / r;
+  else if (cost == 3) wt = (r < param) ? 1.0 : 0.0;
+  else if (cost == 4) { const double s = 1.0 + r2; wt = 1.0 / (s * s); }
+  else if (cost == 5) {
+    const double c2 = param * param;
+    if (r2 >= c2 * (mu + 1.0) / mu) wt = 0.0;
+    else if (r2 <= c2 * mu / (mu + 1.0)) wt = 1.0;
+    else wt = sqrt(c2 * mu * (mu + 1.0) / r2) - mu;
+  }
+  w[e] = wt;
+}
+
+// ---------------------------------------------------------------------------------------------
 // launchers
 // ---------------------------------------------------------------------------------------------
 // Dynamic shared memory of one launch: the reduction scratch, plus what the launch's preconditioner stages (the dense
@@ -1594,5 +1671,25 @@ cudaError_t launch_build_G(int r, int dh, int nposes, const int *pose_ids, const
   if (!ok) return cudaErrorInvalidValue;
   return cudaGetLastError();
 }
+
+cudaError_t launch_assemble_Q(int64_t nb, const int *cptr, const int2 *contrib, const double *eT, const double *eom, const double *ew,
+                              const double *sblk, double *bval, cudaStream_t stream) {
+  if (nb > 0) k_assemble_Q<<<(unsigned)((nb * 16 + 255) / 256), 256, 0, stream>>>(nb, cptr, contrib, eT, eom, ew, sblk, bval);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_edge_weights(int r, int dh, int64_t m, const int *p1, const int *p2, const double *eT, const double *eom,
+                                const int *fixed, const double *X, int cost, double mu, double param, double *w, double *resid,
+                                cudaStream_t stream) {
+  if (m <= 0) return cudaSuccess;
+  bool ok = false;
+  DPGO_DISPATCH(r, dh, {
+    k_edge_weights<R, DH><<<(unsigned)((m + 127) / 128), 128, 0, stream>>>(m, p1, p2, eT, eom, fixed, X, cost, mu, param, w, resid);
+    ok = true;
+  });
+  if (!ok) return cudaErrorInvalidValue;
+  return cudaGetLastError();
+}
+
 
 }  // namespace dpgo

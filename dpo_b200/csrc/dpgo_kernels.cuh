@@ -105,6 +105,11 @@ cudaError_t launch_pack_tiles(int ts, int count, const int *pose, const double *
 cudaError_t launch_build_G(int r, int dh, int nposes, const int *pose_ids, const int *pose_ptr, const int *edge_slot,
                            const int *edge_out, const double *edge_T, const double *edge_om, const double *gathered,
                            double *G, cudaStream_t stream);
+cudaError_t launch_assemble_Q(int64_t nb, const int *cptr, const int2 *contrib, const double *eT, const double *eom, const double *ew,
+                              const double *sblk, double *bval, cudaStream_t stream);
+cudaError_t launch_edge_weights(int r, int dh, int64_t m, const int *p1, const int *p2, const double *eT, const double *eom,
+                                const int *fixed, const double *X, int cost, double mu, double param, double *w, double *resid,
+                                cudaStream_t stream);
 cudaError_t launch_pack_sym(const double *pinv, int N, int nchunks, const int *segptr, int nseg, const long long *off, double *ppack,
                             cudaStream_t stream);
 cudaError_t launch_bsr_to_dense(int n, int dh, int64_t nb, const int *rowptr, const int *bcol, const double *bval,

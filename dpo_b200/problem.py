@@ -103,6 +103,46 @@ class QuadraticProblem:
         capi.check(self._lib.dpgo_problem_set_Q_blocks(self._h, brow.shape[0], capi.iptr(brow), capi.iptr(bcol),
                                                        capi.dptr(blocks), self._precond_mask))
 
+    ROBUST = {"L2": 0, "L1": 1, "Huber": 2, "TLS": 3, "GM": 4, "GNC_TLS": 5}
+
+    def setEdges(self, edges, static_pose=None, static_blocks=None, fixed=None, preconditioners=None) -> None:
+        """Q assembled on the device from raw edge records (ref constructConnectionLaplacianSE, src/DPGO_utils.cpp:199-271;
+        diagonal terms of PGOAgent::constructQMatrix, src/PGOAgent.cpp:746-775 as `static` blocks at (pose, pose)).
+        `edges`: posegraph.EdgeSet with local pose ids; `fixed`: per-edge flags whose weights robustReweight leaves alone."""
+        if preconditioners is not None:
+            self._precond_mask = 0
+            for m in preconditioners:
+                self._precond_mask |= 1 << m
+        dh = self.d + 1
+        p1 = np.ascontiguousarray(edges.p1, dtype=np.int32)
+        p2 = np.ascontiguousarray(edges.p2, dtype=np.int32)
+        R = np.ascontiguousarray(edges.R, dtype=np.float64)
+        t = np.ascontiguousarray(edges.t, dtype=np.float64)
+        ka = np.ascontiguousarray(edges.kappa, dtype=np.float64)
+        ta = np.ascontiguousarray(edges.tau, dtype=np.float64)
+        w = np.ascontiguousarray(edges.weight, dtype=np.float64)
+        fx = None if fixed is None else np.ascontiguousarray(fixed, dtype=np.int32)
+        ns = 0 if static_pose is None else len(static_pose)
+        sp_ = None if ns == 0 else np.ascontiguousarray(static_pose, dtype=np.int32)
+        sb_ = None if ns == 0 else np.ascontiguousarray(static_blocks, dtype=np.float64).reshape(ns, dh, dh)
+        capi.check(self._lib.dpgo_problem_set_edges(
+            self._h, len(p1), capi.iptr(p1), capi.iptr(p2), capi.dptr(R), capi.dptr(t), capi.dptr(ka), capi.dptr(ta), capi.dptr(w),
+            None if fx is None else capi.iptr(fx), ns, None if sp_ is None else capi.iptr(sp_),
+            None if sb_ is None else capi.dptr(sb_), self._precond_mask))
+        self._num_edges = len(p1)
+
+    def robustReweight(self, cost: str, mu: float = 1.0, param: float = 1.0):
+        """Weights of the non-fixed edges at the RESIDENT iterate (upload_X first), Q re-assembled on the device.
+        ref PGOAgent::updateLoopClosuresWeights, src/PGOAgent.cpp:1181-1245.  Returns (weights, squared residuals)."""
+        m = getattr(self, "_num_edges", 0)
+        w, r2 = np.zeros(max(m, 1)), np.zeros(max(m, 1))
+        capi.check(self._lib.dpgo_problem_robust_reweight(self._h, self.ROBUST[cost], float(mu), float(param), capi.dptr(w), capi.dptr(r2)))
+        return w[:m], r2[:m]
+
+    def setEdgeWeights(self, weights) -> None:
+        w = np.ascontiguousarray(weights, dtype=np.float64)
+        capi.check(self._lib.dpgo_problem_set_edge_weights(self._h, capi.dptr(w)))
+
     def setG(self, G) -> None:
         """G: dense (r, (d+1)n) array, scipy sparse matrix, or None to clear.  ref: setG, .cpp:44-48."""
         if G is None:

@@ -129,6 +129,25 @@ DPGO_API int dpgo_problem_set_Q_csr(dpgo_problem_t *p, int nrows, const int32_t 
  * src/DPGO_utils.cpp:264-271, src/PGOAgent.cpp:720-781). */
 DPGO_API int dpgo_problem_set_Q_blocks(dpgo_problem_t *p, int64_t nb, const int32_t *brow, const int32_t *bcol,
                               const double *blocks, unsigned precond_mask);
+/* Q assembled ON THE DEVICE from raw edge records (ref constructConnectionLaplacianSE, src/DPGO_utils.cpp:199-271, and the
+ * shared-edge diagonal terms of PGOAgent::constructQMatrix, src/PGOAgent.cpp:720-781).  m private edges p1 -> p2 (local pose
+ * ids), R: m x d x d row-major, t: m x d, kappa / tau / weight: m (weight NULL = 1), fixed_weight: m flags (NULL = none; a
+ * fixed edge keeps its weight in dpgo_problem_robust_reweight: the reference's isKnownInlier, e.g. odometry); plus
+ * num_static blocks added at (static_pose, static_pose), (d+1)x(d+1) row-major each (already weighted).  The block pattern
+ * is built on the host once, the values by k_assemble_Q; re-assembly after a weight change keeps the pattern. */
+DPGO_API int dpgo_problem_set_edges(dpgo_problem_t *p, int64_t m, const int32_t *p1, const int32_t *p2, const double *R,
+                                    const double *t, const double *kappa, const double *tau, const double *weight,
+                                    const int32_t *fixed_weight, int64_t num_static, const int32_t *static_pose,
+                                    const double *static_blocks, unsigned precond_mask);
+/* Robust re-weighting at the resident iterate (ref PGOAgent::updateLoopClosuresWeights, src/PGOAgent.cpp:1181-1245;
+ * RobustCost::weight, src/DPGO_robust.cpp:23-66): w_e = weight(sqrt(kappa |Y_i R - Y_j|^2 + tau |p_j - p_i - Y_i t|^2)) for
+ * every non-fixed edge, then Q is re-assembled on the device and the preconditioners are refreshed.
+ * cost: 0 L2, 1 L1, 2 Huber(param), 3 TLS(param), 4 Geman-McClure, 5 GNC_TLS(mu, param = cbar).
+ * weights_host / residuals2_host (nullable): the new weights and the squared residuals, m each. */
+DPGO_API int dpgo_problem_robust_reweight(dpgo_problem_t *p, int cost, double mu, double param, double *weights_host,
+                                          double *residuals2_host);
+/* replace the edge weights (m values) and re-assemble Q on the device */
+DPGO_API int dpgo_problem_set_edge_weights(dpgo_problem_t *p, const double *weights_host);
 /* ref: QuadraticProblem::setG, src/QuadraticProblem.cpp:44-48.  Dense r x (d+1)n column-major,
  * or the reference's sparse form (row-major CSR with r rows).  NULL / nnz == 0 clears G. */
 DPGO_API int dpgo_problem_set_G_dense(dpgo_problem_t *p, const double *G_host);
