@@ -70,20 +70,21 @@ __device__ __forceinline__ double pick3(double p0, double p1, double p2, int idx
 // Returns Out_j[a,c] in lane (a,c) (garbage-free zero in invalid lanes).  If ONFLY, the operand
 // is formed on the fly as P_i = -Zs_i + beta * Dold_i (the tCG direction update fused into the
 // Hessian-vector product so no separate pass / grid barrier is needed for it).
+// rowptr / bcol are read with plain (generic) loads: the persistent kernel passes its shared-memory copy of the CTA's
+// row range (local block offsets, bval rebased accordingly), the stand-alone kernel the global arrays.
 template <int R, int DH, bool COHERENT, bool ONFLY>
-__device__ __forceinline__ double gather_tile(const int *__restrict__ rowptr, const int *__restrict__ bcol,
+__device__ __forceinline__ double gather_tile(const int *rowptr, const int *bcol,
                                               const double *__restrict__ bval, const double *P,
                                               const double *Dold, double beta, int j, int a, int k) {
   constexpr int TS = R * DH;
   const bool valid = (a < R) && (k < DH);
   const int off = k * R + a;
   double acc0 = 0.0, acc1 = 0.0, acc2 = 0.0, acc3 = 0.0;
-  const int b0 = ld_const(rowptr + j), b1 = ld_const(rowptr + j + 1);
+  const int b0 = rowptr[j], b1 = rowptr[j + 1];
   int b = b0;
   // 4-deep batches: all loads of a batch are issued before the first FMA (memory-level parallelism)
   for (; b + 4 <= b1; b += 4) {
-    int i0 = ld_const(bcol + b), i1 = ld_const(bcol + b + 1), i2 = ld_const(bcol + b + 2),
-        i3 = ld_const(bcol + b + 3);
+    int i0 = bcol[b], i1 = bcol[b + 1], i2 = bcol[b + 2], i3 = bcol[b + 3];
     double x0 = 0, x1 = 0, x2 = 0, x3 = 0;
     if (valid) {
       x0 = ld_vec<COHERENT>(P + (size_t)i0 * TS + off);
@@ -111,7 +112,7 @@ __device__ __forceinline__ double gather_tile(const int *__restrict__ rowptr, co
     acc0 = fma(x3, q3a.x, acc0); acc1 = fma(x3, q3a.y, acc1); acc2 = fma(x3, q3b.x, acc2); acc3 = fma(x3, q3b.y, acc3);
   }
   for (; b < b1; ++b) {
-    int i0 = ld_const(bcol + b);
+    int i0 = bcol[b];
     double x0 = 0;
     if (valid) {
       x0 = ld_vec<COHERENT>(P + (size_t)i0 * TS + off);

@@ -67,12 +67,21 @@ __device__ __forceinline__ void phase_end(const KParams &kp, BlockCtx &bc, doubl
 }
 
 // row iteration helper: warp-uniform loop, sub-groups past the end run with active == false
+// The CTA's row range and (when it fits) a shared-memory copy of its block-CSR structure, set up once per launch: the
+// sparse phases then start their X gathers without first waiting for two dependent global loads (row pointer, indices).
+struct CtaRows {
+  int r0, r1;
+  const int *rowptr;      // indexable by the global row j (shared copy: local block offsets; else the global array)
+  const int *bcol;        // indexable by those block offsets
+  const double *bval;     // rebased to match
+};
+
 template <int R> struct RowIter {
   static constexpr int SG = SubGroup<R>::SG;
   int r0, r1, stride, jb, sgw, a, c;
-  __device__ RowIter(const KParams &kp) {
-    r0 = ld_const(kp.cta_rows + blockIdx.x);
-    r1 = ld_const(kp.cta_rows + blockIdx.x + 1);
+  __device__ RowIter(const CtaRows &cr) {
+    r0 = cr.r0;
+    r1 = cr.r1;
     const int lane = threadIdx.x & 31;
     constexpr int SGW = 32 / SG;                 // sub-groups per warp
     sgw = lane / SG;
@@ -93,11 +102,11 @@ template <int R> struct RowIter {
 // acc: [0] <XQ,X>  [1] <X,G>  [2] |RG|^2  [3] <Z0,RG>
 // ---------------------------------------------------------------------------------------------
 template <int R, int DH>
-__device__ void phase_eval(const KParams &kp, int cb, bool save_xin, int precond, double (&acc)[NRED]) {
+__device__ void phase_eval(const KParams &kp, const CtaRows &cr, int cb, bool save_xin, int precond, double (&acc)[NRED]) {
   constexpr int TS = R * DH;
   const double *X = kp.v[V_X0 + cb];
   double *EG = kp.v[V_EG0 + cb], *RG = kp.v[V_RG0 + cb], *Z0 = kp.v[V_Z00 + cb], *S = kp.S[cb];
-  RowIter<R> it(kp);
+  RowIter<R> it(cr);
   const bool valid = (it.a < R) && (it.c < DH);
   const int e = it.c * R + it.a;
   for (int jb = it.jb; jb < it.r1; jb += it.stride) {
@@ -105,7 +114,7 @@ __device__ void phase_eval(const KParams &kp, int cb, bool save_xin, int precond
     const bool act = (j < it.r1);
     const int js = act ? j : it.r1 - 1;
     const bool ld = act && valid;
-    double xq = gather_tile<R, DH, true, false>(kp.rowptr, kp.bcol, kp.bval, X, nullptr, 0.0, js, it.a, it.c);
+    double xq = gather_tile<R, DH, true, false>(cr.rowptr, cr.bcol, cr.bval, X, nullptr, 0.0, js, it.a, it.c);
     const size_t idx = (size_t)js * TS + e;
     const double x = ld ? __ldcg(X + idx) : 0.0;
     const double g = ld ? __ldcg(kp.G + idx) : 0.0;
@@ -148,33 +157,30 @@ __device__ void phase_eval(const KParams &kp, int cb, bool save_xin, int precond
 // If onfly == false the operand is read as is from `zsrc` (single-operation entry point).
 // ---------------------------------------------------------------------------------------------
 template <int R, int DH>
-__device__ void phase_hess(const KParams &kp, int cb, const double *zsrc, const double *dold, double *dnew,
+__device__ void phase_hess(const KParams &kp, const CtaRows &cr, int cb, const double *zsrc, const double *dold, double *dnew,
                            double beta, bool onfly, double (&acc)[NRED]) {
   constexpr int TS = R * DH;
   constexpr int D = DH - 1;
   const double *X = kp.v[V_X0 + cb];
   const double *S = kp.S[cb];
   double *HD = kp.v[V_HD];
-  RowIter<R> it(kp);
+  RowIter<R> it(cr);
   const bool valid = (it.a < R) && (it.c < DH);
   const int e = it.c * R + it.a;
+  const bool ticking = (kp.phase_ns != nullptr) && blockIdx.x == 0 && threadIdx.x == 0;
+  unsigned long long th0 = 0, th1 = 0;
+  if (ticking) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(th0));
   for (int jb = it.jb; jb < it.r1; jb += it.stride) {
     const int j = jb + it.sgw;
     const bool act = (j < it.r1);
     const int js = act ? j : it.r1 - 1;
     const bool ld = act && valid;
-    double hq;
-    if (onfly) hq = gather_tile<R, DH, true, true>(kp.rowptr, kp.bcol, kp.bval, zsrc, dold, beta, js, it.a, it.c);
-    else hq = gather_tile<R, DH, true, false>(kp.rowptr, kp.bcol, kp.bval, zsrc, nullptr, 0.0, js, it.a, it.c);
+    // the row's own operands first: these loads are independent of the gather and overlap its round trips
     const size_t idx = (size_t)js * TS + e;
-    double dl = 0.0;
+    double dl = 0.0, dprev = 0.0;
     if (ld) {
       dl = __ldcg(zsrc + idx);
-      if (onfly) {
-        dl = -dl;
-        if (beta != 0.0) dl = fma(beta, __ldcg(dold + idx), dl);
-        dnew[idx] = dl;
-      }
+      if (onfly && beta != 0.0) dprev = __ldcg(dold + idx);
     }
     const double x = ld ? __ldcg(X + idx) : 0.0;
     const bool rot = ld && (it.c < D);
@@ -182,6 +188,15 @@ __device__ void phase_hess(const KParams &kp, int cb, const double *zsrc, const 
     if (rot) {
       const double *s = S + (size_t)js * 9 + it.c * 3;
       s0 = __ldcg(s); s1 = __ldcg(s + 1); s2 = __ldcg(s + 2);
+    }
+    double hq;
+    if (onfly) hq = gather_tile<R, DH, true, true>(cr.rowptr, cr.bcol, cr.bval, zsrc, dold, beta, js, it.a, it.c);
+    else hq = gather_tile<R, DH, true, false>(cr.rowptr, cr.bcol, cr.bval, zsrc, nullptr, 0.0, js, it.a, it.c);
+    if (ticking && jb == it.jb) { asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(th1)); kp.phase_ns[27] += th1 - th0; }
+    if (ld && onfly) {
+      dl = -dl;
+      if (beta != 0.0) dl = fma(beta, dprev, dl);
+      dnew[idx] = dl;
     }
     const double dr = rot ? dl : 0.0;
     const double d0 = quad_get(dr, 0), d1 = quad_get(dr, 1), d2 = (D > 2) ? quad_get(dr, 2) : 0.0;
@@ -194,6 +209,7 @@ __device__ void phase_hess(const KParams &kp, int cb, const double *zsrc, const 
       acc[0] = fma(dl, hd, acc[0]);
     }
   }
+  if (ticking) { asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(th1)); kp.phase_ns[28] += th1 - th0; }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -201,14 +217,14 @@ __device__ void phase_hess(const KParams &kp, int cb, const double *zsrc, const 
 // z = P_X(M^-1 res), <z,res>.   acc: [0] |res|^2  [1] <z,res>
 // ---------------------------------------------------------------------------------------------
 template <int R, int DH>
-__device__ void phase_update(const KParams &kp, int cb, const double *dcur, double alpha, bool first, int precond,
+__device__ void phase_update(const KParams &kp, const CtaRows &cr, int cb, const double *dcur, double alpha, bool first, int precond,
                              double (&acc)[NRED]) {
   constexpr int TS = R * DH;
   const double *X = kp.v[V_X0 + cb];
   const double *RG = kp.v[V_RG0 + cb];
   double *ETA = kp.v[V_ETA], *RES = kp.v[V_RES], *Z = kp.v[V_Z];
   const double *HD = kp.v[V_HD];
-  RowIter<R> it(kp);
+  RowIter<R> it(cr);
   const bool valid = (it.a < R) && (it.c < DH);
   const int e = it.c * R + it.a;
   for (int jb = it.jb; jb < it.r1; jb += it.stride) {
@@ -619,7 +635,7 @@ template <int R> __device__ void phase_dense_sym(const KParams &kp, const double
 // [r0*TS, r1*TS): thread (e, p) sums slabs p, p+P, ... of element e with 32 independent L2 loads in flight (P = how
 // many times the range fits into the CTA), fixed order; step 2 combines the P parts in order and projects per pose.
 template <int R, int DH>
-__device__ void phase_pz(const KParams &kp, int cb, const double *V, double *Zout, double *sT, double (&acc)[NRED]) {
+__device__ void phase_pz(const KParams &kp, const CtaRows &cr, int cb, const double *V, double *Zout, double *sT, double (&acc)[NRED]) {
   constexpr int TS = R * DH;
   constexpr int PZ_TILE = DENSE_PER_MAX * R;          // elements staged per round (sT = the V staging area of the dense phases)
   const int nseg_sym = (kp.N + SYM_SEG - 1) / SYM_SEG;
@@ -627,7 +643,7 @@ __device__ void phase_pz(const KParams &kp, int cb, const double *V, double *Zou
   const bool symm = kp.sym_ok != 0;
   const int nslabs_full = (kp.N + kp.dense_per - 1) / kp.dense_per;
   const size_t stride = (size_t)R * kp.N;
-  RowIter<R> it(kp);
+  RowIter<R> it(cr);
   const bool valid = (it.a < R) && (it.c < DH);
   const int e = it.c * R + it.a;
   const int rows_per_round = PZ_TILE / TS;
@@ -897,13 +913,13 @@ __device__ void phase_nd(const KParams &kp, int ph, const double *V, int cb, dou
 // mode 2: eta read as is from V_AUX (single-operation entry point).
 // ---------------------------------------------------------------------------------------------
 template <int R, int DH>
-__device__ void phase_retract(const KParams &kp, int cb, int mode, const double *dcur, double tau, bool eta_zero,
+__device__ void phase_retract(const KParams &kp, const CtaRows &cr, int cb, int mode, const double *dcur, double tau, bool eta_zero,
                               double step, double (&acc)[NRED]) {
   constexpr int TS = R * DH;
   const double *X = kp.v[V_X0 + cb];
   const double *RG = kp.v[V_RG0 + cb];
   double *X2 = kp.v[V_X0 + (1 - cb)];
-  RowIter<R> it(kp);
+  RowIter<R> it(cr);
   const bool valid = (it.a < R) && (it.c < DH);
   const int e = it.c * R + it.a;
   for (int jb = it.jb; jb < it.r1; jb += it.stride) {
@@ -940,9 +956,9 @@ __device__ void phase_retract(const KParams &kp, int cb, int mode, const double 
 
 // Final phase: make X0 hold the result and accumulate |X_out - X_in|^2 (ref: relativeChange,
 // src/QuadraticOptimizer.cpp:54).
-template <int R, int DH> __device__ void phase_final(const KParams &kp, int cur, double (&acc)[NRED]) {
+template <int R, int DH> __device__ void phase_final(const KParams &kp, const CtaRows &cr, int cur, double (&acc)[NRED]) {
   constexpr int TS = R * DH;
-  RowIter<R> it(kp);
+  RowIter<R> it(cr);
   const bool valid = (it.a < R) && (it.c < DH);
   const int e = it.c * R + it.a;
   for (int jb = it.jb; jb < it.r1; jb += it.stride) {
@@ -970,7 +986,27 @@ template <int R, int DH> __global__ void __launch_bounds__(OPT_THREADS, 1) k_opt
   BlockCtx bc;
   bc.sm_warp = smem;
   bc.sm_out = smem + (OPT_THREADS / 32) * NRED;
-  double *sV = bc.sm_out + NRED;                // dense-preconditioner staging (dense_per * R doubles)
+  // the CTA's rows and, when they fit, its slice of the block-CSR structure in shared memory (SP_CACHE_INTS ints)
+  int *sp_ints = reinterpret_cast<int *>(bc.sm_out + NRED);
+  CtaRows cr;
+  cr.r0 = ld_const(kp.cta_rows + blockIdx.x);
+  cr.r1 = ld_const(kp.cta_rows + blockIdx.x + 1);
+  cr.rowptr = kp.rowptr;
+  cr.bcol = kp.bcol;
+  cr.bval = kp.bval;
+  {
+    const int nrows = cr.r1 - cr.r0;
+    const int blk0 = (nrows > 0) ? ld_const(kp.rowptr + cr.r0) : 0, blk1 = (nrows > 0) ? ld_const(kp.rowptr + cr.r1) : 0;
+    if (nrows > 0 && nrows + 1 + (blk1 - blk0) <= SP_CACHE_INTS) {
+      for (int q = threadIdx.x; q <= nrows; q += blockDim.x) sp_ints[q] = ld_const(kp.rowptr + cr.r0 + q) - blk0;
+      for (int q = threadIdx.x; q < blk1 - blk0; q += blockDim.x) sp_ints[nrows + 1 + q] = ld_const(kp.bcol + blk0 + q);
+      cr.rowptr = sp_ints - cr.r0;              // indexed by the global row
+      cr.bcol = sp_ints + nrows + 1;            // indexed by the local block offset
+      cr.bval = kp.bval + (size_t)blk0 * 16;
+    }
+    __syncthreads();
+  }
+  double *sV = reinterpret_cast<double *>(sp_ints + SP_CACHE_INTS);   // dense-preconditioner staging / sparse-plan areas
   DenseRing ring;
   ring.buf = sV + (size_t)DENSE_PER_MAX * R;    // 16-byte aligned: every preceding block is a multiple of 2 doubles
   ring.full = reinterpret_cast<uint64_t *>(ring.buf + (size_t)DENSE_RING_DOUBLES);
@@ -1032,7 +1068,7 @@ template <int R, int DH> __global__ void __launch_bounds__(OPT_THREADS, 1) k_opt
       else phase_dense<R>(kp, Vv, sV);
       zero(acc); phase_end<0>(kp, bc, acc);
       tick(1);
-      zero(acc); phase_pz<R, DH>(kp, cbx, Vv, Zout, sV, acc);
+      zero(acc); phase_pz<R, DH>(kp, cr, cbx, Vv, Zout, sV, acc);
       phase_end<1>(kp, bc, acc);
       tick(2);
     }
@@ -1057,7 +1093,7 @@ template <int R, int DH> __global__ void __launch_bounds__(OPT_THREADS, 1) k_opt
     } else {
       // reuse phase_update with res := AUX (first = false, alpha = 0 would need RES); do it directly
       constexpr int TS = R * DH;
-      RowIter<R> it(kp);
+      RowIter<R> it(cr);
       const bool valid = (it.a < R) && (it.c < DH);
       const int e = it.c * R + it.a;
       for (int jb = it.jb; jb < it.r1; jb += it.stride) {
@@ -1080,7 +1116,7 @@ template <int R, int DH> __global__ void __launch_bounds__(OPT_THREADS, 1) k_opt
   }
   if (kp.op == OP_RETRACT) {
     zero(acc);
-    phase_retract<R, DH>(kp, 0, 2, nullptr, 0.0, false, 0.0, acc);
+    phase_retract<R, DH>(kp, cr, 0, 2, nullptr, 0.0, false, 0.0, acc);
     phase_end(kp, bc, acc);
     if (blockIdx.x == 0 && threadIdx.x == 0) *kp.bar_epoch = bc.epoch;
     return;
@@ -1088,7 +1124,7 @@ template <int R, int DH> __global__ void __launch_bounds__(OPT_THREADS, 1) k_opt
 
   // ---- statistics at the input point (ref: src/QuadraticOptimizer.cpp:36-37) -------------------
   zero(acc);
-  phase_eval<R, DH>(kp, 0, true, precond, acc);
+  phase_eval<R, DH>(kp, cr, 0, true, precond, acc);
   phase_end(kp, bc, acc);
   tick(0);
   res.spmv_passes++;
@@ -1109,7 +1145,7 @@ template <int R, int DH> __global__ void __launch_bounds__(OPT_THREADS, 1) k_opt
   }
   if (kp.op == OP_RHESS) {
     zero(acc);
-    phase_hess<R, DH>(kp, 0, kp.v[V_AUX], nullptr, nullptr, 0.0, false, acc);
+    phase_hess<R, DH>(kp, cr, 0, kp.v[V_AUX], nullptr, nullptr, 0.0, false, acc);
     phase_end(kp, bc, acc);
     if (blockIdx.x == 0 && threadIdx.x == 0) { *kp.result = res; *kp.bar_epoch = bc.epoch; }
     return;
@@ -1118,10 +1154,10 @@ template <int R, int DH> __global__ void __launch_bounds__(OPT_THREADS, 1) k_opt
   if (prm.algorithm == DPGO_ALG_RGD) {
     // ---- one fixed-step Riemannian gradient-descent step (ref :124-149) ----------------------
     zero(acc);
-    phase_retract<R, DH>(kp, 0, 1, nullptr, 0.0, false, prm.rgd_stepsize, acc);
+    phase_retract<R, DH>(kp, cr, 0, 1, nullptr, 0.0, false, prm.rgd_stepsize, acc);
     phase_end(kp, bc, acc);
     zero(acc);
-    phase_eval<R, DH>(kp, 1, false, DPGO_PRECOND_NONE, acc);
+    phase_eval<R, DH>(kp, cr, 1, false, DPGO_PRECOND_NONE, acc);
     phase_end(kp, bc, acc);
     res.spmv_passes++;
     res.f_opt = 0.5 * acc[0] + acc[1];
@@ -1157,7 +1193,7 @@ template <int R, int DH> __global__ void __launch_bounds__(OPT_THREADS, 1) k_opt
       for (int j = 0; j < prm.tr_max_inner; ++j) {
         double *dnew = kp.v[V_D0 + (1 - pd)];
         zero(acc);
-        phase_hess<R, DH>(kp, cb, zsrc, kp.v[V_D0 + pd], dnew, beta, true, acc);
+        phase_hess<R, DH>(kp, cr, cb, zsrc, kp.v[V_D0 + pd], dnew, beta, true, acc);
         phase_end<1>(kp, bc, acc);
         tick(3);
         res.spmv_passes++;
@@ -1174,7 +1210,7 @@ template <int R, int DH> __global__ void __launch_bounds__(OPT_THREADS, 1) k_opt
         }
         e_Pe = e_new;
         zero(acc);
-        phase_update<R, DH>(kp, cb, dcur, alpha, eta_zero, precond, acc);
+        phase_update<R, DH>(kp, cr, cb, dcur, alpha, eta_zero, precond, acc);
         phase_end<2>(kp, bc, acc);
         tick(4);
         eta_zero = false;
@@ -1200,12 +1236,12 @@ template <int R, int DH> __global__ void __launch_bounds__(OPT_THREADS, 1) k_opt
       res.outer_iterations++;
       // -- candidate point, model decrease, actual decrease
       zero(acc);
-      phase_retract<R, DH>(kp, cb, 0, dcur, tau, eta_zero, 0.0, acc);
+      phase_retract<R, DH>(kp, cr, cb, 0, dcur, tau, eta_zero, 0.0, acc);
       phase_end<2>(kp, bc, acc);
       tick(5);
       const double denom = -acc[0] - 0.5 * acc[1];
       zero(acc);
-      phase_eval<R, DH>(kp, 1 - cb, false, precond, acc);
+      phase_eval<R, DH>(kp, cr, 1 - cb, false, precond, acc);
       phase_end(kp, bc, acc);
       tick(0);
       res.spmv_passes++;
@@ -1242,7 +1278,7 @@ template <int R, int DH> __global__ void __launch_bounds__(OPT_THREADS, 1) k_opt
   }
 
   zero(acc);
-  phase_final<R, DH>(kp, cur, acc);
+  phase_final<R, DH>(kp, cr, cur, acc);
   phase_end<1>(kp, bc, acc);
   tick(6);
   res.relative_change = sqrt(acc[0] / (double)kp.n);
@@ -1492,7 +1528,7 @@ __global__ void k_edge_weights(int64_t m, const int *__restrict__ p1, const int 
 // ring or the sparse plan's tiles and slots).  Asking for no more than needed leaves the rest of the SM's 228 KB to L1,
 // which now keeps the constant data (block-CSR, plan records) across phases.
 template <int R, int DH> static size_t optimize_smem_doubles(const KParams &kp, bool max_only) {
-  const size_t base = (OPT_THREADS / 32) * NRED + NRED;
+  const size_t base = (OPT_THREADS / 32) * NRED + NRED + SP_CACHE_INTS / 2;
   const size_t dense = (size_t)DENSE_PER_MAX * R + (size_t)DENSE_RING_DOUBLES + 2 * DENSE_NST + (size_t)SYM_META_DOUBLES;
   if (max_only || kp.prm.precond == DPGO_PRECOND_DENSE_EXACT) return base + dense;
   if (kp.prm.precond == DPGO_PRECOND_SPARSE_EXACT)
@@ -1532,7 +1568,7 @@ template <int R, int DH> static cudaError_t launch_optimize_t(const KParams &kp_
 }
 
 template <int R, int DH> static int max_grid_t(int device) {
-  const size_t smem = ((OPT_THREADS / 32) * NRED + NRED + (size_t)DENSE_PER_MAX * R + (size_t)DENSE_RING_DOUBLES + 2 * DENSE_NST + (size_t)SYM_META_DOUBLES) * sizeof(double);
+  const size_t smem = ((OPT_THREADS / 32) * NRED + NRED + SP_CACHE_INTS / 2 + (size_t)DENSE_PER_MAX * R + (size_t)DENSE_RING_DOUBLES + 2 * DENSE_NST + (size_t)SYM_META_DOUBLES) * sizeof(double);
   cudaFuncSetAttribute(k_optimize<R, DH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   int per_sm = 0, sms = 0;
   if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_optimize<R, DH>, OPT_THREADS, smem) != cudaSuccess) return 0;

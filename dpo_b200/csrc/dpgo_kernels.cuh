@@ -36,6 +36,7 @@ constexpr int OPT_THREADS = 512;   // persistent kernel block size
 constexpr int SPMV_GROUP_BLOCKS = 192;  // blocks per row group of the TMA-fed SpMV (24 KB of Q per smem stage)
 constexpr int ND_YCAP_TILES = 600;  // sparse exact preconditioner: pose tiles of a phase's input vector staged in shared memory per step
 constexpr int ND_SLOT_CAP = 240;    // ... and partial-sum slots (8 rows x r doubles) per step
+constexpr int SP_CACHE_INTS = 2048;  // shared-memory copy of a CTA's block-CSR structure (row pointers + block columns), 8 KB
 constexpr int DENSE_PER_MAX = 512;  // max rows of the dense inverse one CTA owns (smem staging of V): N <= 75k at 148 CTAs
 
 // sparse exact preconditioner (nd_precond.h): the static plan and the panel blob in HBM / L2

@@ -75,6 +75,7 @@ def main():
            "ms_per_step_by_kind": {k: ms[i] / args.steps for i, k in enumerate(KINDS) if ms[i] > 0},
            "us_per_dense_apply": 1e3 * ms[1] / max(applies, 1), "us_per_partial_sum": 1e3 * ms[2] / max(applies, 1),
            "us_per_hessian": 1e3 * ms[3] / max(passes - 2 * args.steps, 1)}
+    out["hessian_cta0_us"] = {"first_gather": 1e3 * ms[27] / max(passes - 2 * args.steps, 1), "whole_loop": 1e3 * ms[28] / max(passes - 2 * args.steps, 1)}
     if args.precond == "exact":
         out["nd"] = prob.nd_info()
         out["us_per_apply_by_nd_phase"] = [1e3 * ms[8 + k] / max(applies, 1) for k in range(out["nd"]["phases"])]
