@@ -222,23 +222,14 @@ __device__ __forceinline__ unsigned ld_relaxed_u32(const unsigned *p) {
   asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
   return v;
 }
-// Release side: red.release (MEMBAR.GPU + RED) publishes every write of this CTA (ordered before it by the bar.sync).
+// Grid-wide phase end of the persistent kernel (phase_end in dpgo_kernels.cu).
+// Release side: red.release (MEMBAR.GPU + RED) publishes every write of the CTA (ordered before it by a bar.sync).
 // Acquire side: by default the poll is a RELAXED gpu-scope load.  An acquire load would add CCTL.IVALL, i.e. drop the
 // SM's whole L1 at every phase end -- and with it the constant data the phases re-read all the time (block-CSR
 // indices and blocks, plan records).  That invalidation protects weak loads of data other SMs rewrite; this kernel
 // has none: every vector / workspace another CTA may have written is read with ld.global.cg (L2) or ld.relaxed.gpu,
 // never through L1, and read-only data is never rewritten during a launch.  Ordering of those L2 reads after the
 // poll: the poll loop's exit branch depends on the loaded value and the other threads wait at the bar.sync behind it.
-// strict != 0 restores the acquire poll (A/B: DPGO_STRICT_ACQUIRE=1).
-__device__ __forceinline__ void grid_barrier(unsigned *counter, unsigned &epoch, int strict = 0) {
-  __syncthreads();
-  epoch += gridDim.x;
-  if (threadIdx.x == 0) {
-    asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(counter) : "memory");
-    if (strict) { while ((int)(ld_acquire_u32(counter) - epoch) < 0) { } }
-    else { while ((int)(ld_relaxed_u32(counter) - epoch) < 0) { } }
-  }
-  __syncthreads();
-}
+// KParams::strict_acquire != 0 restores the acquire poll (A/B: DPGO_STRICT_ACQUIRE=1).
 
 }  // namespace dpgo

@@ -22,11 +22,18 @@ namespace dpgo {
 // ---------------------------------------------------------------------------------------------
 struct BlockCtx {
   double *sm_warp;    // [nwarps * NRED]
-  double *sm_out;     // [NRED]
+  double *sm_out;     // [2 * NRED]  totals of the phase, double-buffered by parity
   unsigned epoch;
   int parity;
 };
 
+// The reduction steps around the barrier are kept short (they are pure latency, ~80 times per step): the 16 warp
+// partials are combined by a shuffle tree in warp 0 (fixed order), lane 0 stores the CTA's partials and arrives at the
+// barrier right behind them (the release covers the store), the whole of warp 0 polls the counter (one broadcast request)
+// and goes straight on to fetch all CTAs' partials; the totals are published through a parity-double-buffered shared slot,
+// so a phase end has two bar.syncs, not four.  (A fused variant -- 16-byte {value, phase} packets polled all-to-all, barrier
+// and all-reduce in one round trip -- was measured and is NOT faster: scripts/barrier_bench3.cu, 3.55 vs 3.40 us; with
+// gpu-scope "strong" 16-byte accesses it is 3x slower.)
 template <int NUSED = NRED>
 __device__ __forceinline__ void phase_end(const KParams &kp, BlockCtx &bc, double (&acc)[NRED]) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
@@ -35,38 +42,47 @@ __device__ __forceinline__ void phase_end(const KParams &kp, BlockCtx &bc, doubl
     double v = warp_sum(acc[q]);
     if (lane == 0) bc.sm_warp[warp * NRED + q] = v;
   }
-  if (NUSED > 0) __syncthreads();
+  __syncthreads();                                       // also: every write of this phase is ordered before the release below
+  bc.epoch += gridDim.x;
   double *slot = kp.partials + (size_t)bc.parity * kp.grid * NRED;
-  if ((int)threadIdx.x < NUSED) {
-    double s = 0.0;
-    for (int w = 0; w < nwarps; ++w) s += bc.sm_warp[w * NRED + threadIdx.x];
-    slot[(size_t)blockIdx.x * NRED + threadIdx.x] = s;
-  }
-  grid_barrier(kp.bar_counter, bc.epoch, kp.strict_acquire);
-  if (NUSED > 0) {
-    if (warp == 0) {
+  double *outp = bc.sm_out + bc.parity * NRED;
+  if (warp == 0) {
+    if (NUSED > 0) {
       double s[NUSED > 0 ? NUSED : 1];
 #pragma unroll
-      for (int q = 0; q < NUSED; ++q) s[q] = 0.0;
+      for (int q = 0; q < NUSED; ++q) {
+        double v = (lane < nwarps) ? bc.sm_warp[lane * NRED + q] : 0.0;
+        s[q] = warp_sum(v);                              // fixed shuffle tree over the warps' partials
+      }
+      if (lane == 0) {
+#pragma unroll
+        for (int q = 0; q < NUSED; ++q) slot[(size_t)blockIdx.x * NRED + q] = s[q];
+      }
+    }
+    if (lane == 0) asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(kp.bar_counter) : "memory");
+    if (kp.strict_acquire) { while ((int)(ld_acquire_u32(kp.bar_counter) - bc.epoch) < 0) { } }
+    else { while ((int)(ld_relaxed_u32(kp.bar_counter) - bc.epoch) < 0) { } }
+    if (NUSED > 0) {
+      double t[NUSED > 0 ? NUSED : 1];
+#pragma unroll
+      for (int q = 0; q < NUSED; ++q) t[q] = 0.0;
       for (int c = lane; c < kp.grid; c += 32) {
 #pragma unroll
-        for (int q = 0; q < NUSED; ++q) s[q] += __ldcg(slot + (size_t)c * NRED + q);
+        for (int q = 0; q < NUSED; ++q) t[q] += __ldcg(slot + (size_t)c * NRED + q);
       }
 #pragma unroll
       for (int q = 0; q < NUSED; ++q) {
-        const double t = warp_sum(s[q]);
-        if (lane == 0) bc.sm_out[q] = t;
+        const double v = warp_sum(t[q]);
+        if (lane == 0) outp[q] = v;
       }
     }
-    __syncthreads();
-#pragma unroll
-    for (int q = 0; q < NUSED; ++q) acc[q] = bc.sm_out[q];
-    __syncthreads();           // sm_out / sm_warp may be rewritten by the next phase
   }
+  __syncthreads();
+#pragma unroll
+  for (int q = 0; q < NUSED; ++q) acc[q] = outp[q];
   bc.parity ^= 1;
 }
 
-// row iteration helper: warp-uniform loop, sub-groups past the end run with active == false
 // The CTA's row range and (when it fits) a shared-memory copy of its block-CSR structure, set up once per launch: the
 // sparse phases then start their X gathers without first waiting for two dependent global loads (row pointer, indices).
 struct CtaRows {
@@ -987,7 +1003,7 @@ template <int R, int DH> __global__ void __launch_bounds__(OPT_THREADS, 1) k_opt
   bc.sm_warp = smem;
   bc.sm_out = smem + (OPT_THREADS / 32) * NRED;
   // the CTA's rows and, when they fit, its slice of the block-CSR structure in shared memory (SP_CACHE_INTS ints)
-  int *sp_ints = reinterpret_cast<int *>(bc.sm_out + NRED);
+  int *sp_ints = reinterpret_cast<int *>(bc.sm_out + 2 * NRED);
   CtaRows cr;
   cr.r0 = ld_const(kp.cta_rows + blockIdx.x);
   cr.r1 = ld_const(kp.cta_rows + blockIdx.x + 1);
@@ -1528,7 +1544,7 @@ __global__ void k_edge_weights(int64_t m, const int *__restrict__ p1, const int 
 // ring or the sparse plan's tiles and slots).  Asking for no more than needed leaves the rest of the SM's 228 KB to L1,
 // which now keeps the constant data (block-CSR, plan records) across phases.
 template <int R, int DH> static size_t optimize_smem_doubles(const KParams &kp, bool max_only) {
-  const size_t base = (OPT_THREADS / 32) * NRED + NRED + SP_CACHE_INTS / 2;
+  const size_t base = (OPT_THREADS / 32) * NRED + 2 * NRED + SP_CACHE_INTS / 2;
   const size_t dense = (size_t)DENSE_PER_MAX * R + (size_t)DENSE_RING_DOUBLES + 2 * DENSE_NST + (size_t)SYM_META_DOUBLES;
   if (max_only || kp.prm.precond == DPGO_PRECOND_DENSE_EXACT) return base + dense;
   if (kp.prm.precond == DPGO_PRECOND_SPARSE_EXACT)
@@ -1568,7 +1584,7 @@ template <int R, int DH> static cudaError_t launch_optimize_t(const KParams &kp_
 }
 
 template <int R, int DH> static int max_grid_t(int device) {
-  const size_t smem = ((OPT_THREADS / 32) * NRED + NRED + SP_CACHE_INTS / 2 + (size_t)DENSE_PER_MAX * R + (size_t)DENSE_RING_DOUBLES + 2 * DENSE_NST + (size_t)SYM_META_DOUBLES) * sizeof(double);
+  const size_t smem = ((OPT_THREADS / 32) * NRED + 2 * NRED + SP_CACHE_INTS / 2 + (size_t)DENSE_PER_MAX * R + (size_t)DENSE_RING_DOUBLES + 2 * DENSE_NST + (size_t)SYM_META_DOUBLES) * sizeof(double);
   cudaFuncSetAttribute(k_optimize<R, DH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   int per_sm = 0, sms = 0;
   if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_optimize<R, DH>, OPT_THREADS, smem) != cudaSuccess) return 0;
