@@ -50,7 +50,8 @@ template <class T> void free_dev(T *&p) {
 
 struct dpgo_problem {
   int n = 0, d = 0, r = 0, dh = 0, N = 0, ts = 0;
-  int device = 0, sms = 0, grid = 0, max_grid = 0;
+  int device = 0, sms = 0, grid = 0, max_grid = 0, max_cluster = 0;
+  bool cluster = false;          // the persistent kernel runs as ONE thread-block cluster (small agents)
   cudaStream_t own_stream = nullptr, stream = nullptr;
   // Q in block-CSR
   int64_t nb = 0;
@@ -133,6 +134,7 @@ void fill_kparams(const dpgo_problem *p, dpgo::KParams &kp, int op, const dpgo_o
   if (!p->nd_ready) kp.nd.nphases = 0;
   static const int strict = [] { const char *e = std::getenv("DPGO_STRICT_ACQUIRE"); return (e && e[0] == '1') ? 1 : 0; }();
   kp.strict_acquire = strict;
+  kp.cluster = p->cluster ? 1 : 0;
   kp.smem_doubles = 0;
   kp.phase_ns = p->d_phase_ns;
   kp.prm = prm;
@@ -463,6 +465,17 @@ int build_from_triplets(dpgo_problem *p, std::vector<BlockTriplet> &trip, unsign
   int grid = p->max_grid;
   const bool dense = (precond_mask & ((1u << DPGO_PRECOND_DENSE_EXACT) | (1u << DPGO_PRECOND_SPARSE_EXACT))) != 0;
   if (!dense) grid = std::max(1, std::min(grid, (n + rows_per_pass - 1) / rows_per_pass));
+  // Opt-in experiment (DPGO_CLUSTER_MAX_POSES=<n>, default off): agents of up to n poses run as ONE thread-block cluster
+  // (<= 16 CTAs) whose phase ends are hardware cluster barriers instead of the atomic-counter grid barrier.  Measured on B200
+  // (scripts/phase_times.py --agents 8 / 16, sphere2500): SLOWER than the full grid -- 0.259 vs 0.144 ms per step at 312 poses,
+  // 0.176 vs 0.138 ms at 156 poses: the barrier is cheaper, but 10-16 SMs stream the preconditioner blocks (12.5 / 3.1 MB per
+  // application) 2.5x slower than 148 SMs and every warp walks several rows per sparse phase.
+  static const int cluster_max_poses = [] { const char *e = std::getenv("DPGO_CLUSTER_MAX_POSES"); return e ? std::atoi(e) : 0; }();
+  p->cluster = false;
+  if (p->max_cluster >= 8 && n <= cluster_max_poses && !(precond_mask & (1u << DPGO_PRECOND_DENSE_EXACT))) {
+    grid = std::max(1, std::min(p->max_cluster, (n + rows_per_pass - 1) / rows_per_pass));
+    p->cluster = true;
+  }
   std::vector<int> cta_rows(grid + 1, 0);
   {
     // cost model: blocks + constant epilogue weight per row
@@ -617,6 +630,7 @@ int dpgo_problem_create(int n, int d, int r, int device, dpgo_problem_t **out) {
     return bail(DPGO_ERR_CUDA, "cudaStreamCreate failed");
   p->stream = p->own_stream;
   p->max_grid = dpgo::optimize_max_grid(r, d + 1, device);
+  p->max_cluster = dpgo::optimize_max_cluster(r, d + 1, device);
   if (p->max_grid <= 0) return bail(DPGO_ERR_CUDA, "persistent kernel cannot be made resident on this device");
   const size_t vb = p->vec_bytes();
   for (int i = 0; i < dpgo::V_COUNT; ++i) {

@@ -36,6 +36,7 @@ constexpr int OPT_THREADS = 512;   // persistent kernel block size
 constexpr int SPMV_GROUP_BLOCKS = 192;  // blocks per row group of the TMA-fed SpMV (24 KB of Q per smem stage)
 constexpr int ND_YCAP_TILES = 600;  // sparse exact preconditioner: pose tiles of a phase's input vector staged in shared memory per step
 constexpr int ND_SLOT_CAP = 240;    // ... and partial-sum slots (8 rows x r doubles) per step
+constexpr int ND_SMEM_NEED_SMALL = 16000;   // doubles a small agent's sparse plan needs at most (occupancy query of the cluster launch)
 constexpr int SP_CACHE_INTS = 2048;  // shared-memory copy of a CTA's block-CSR structure (row pointers + block columns), 8 KB
 constexpr int DENSE_PER_MAX = 512;  // max rows of the dense inverse one CTA owns (smem staging of V): N <= 75k at 148 CTAs
 
@@ -87,6 +88,7 @@ struct KParams {
   dpgo_opt_params_t prm;
   dpgo_opt_result_t *result;   // device copy of the result record
   KNd nd;                // sparse exact preconditioner (nd.nphases == 0: not prepared)
+  int cluster;           // 1: the whole grid is ONE thread-block cluster (<= 16 CTAs): phase ends use barrier.cluster
   int strict_acquire;    // 1: the grid barrier polls with ld.acquire (L1 invalidated every phase); 0: relaxed poll (default)
   int smem_doubles;      // dynamic shared memory of this launch, in doubles
   unsigned long long *phase_ns; // diagnostic (nullable): per phase kind, ns seen by CTA 0 (dpgo_debug_phase_times)
@@ -100,6 +102,7 @@ cudaError_t launch_spmv_tma(int r, int dh, int ngroups, const int2 *groups, cons
                             const double *bval, const double *X, const double *G, double *out, int sms,
                             cudaStream_t stream);
 int optimize_max_grid(int r, int dh, int device);   // co-resident CTA count for the persistent kernel
+int optimize_max_cluster(int r, int dh, int device); // largest single-cluster grid (16, 8 or 0) the kernel can be launched with
 cudaError_t launch_stiefel_project(int r, int dh, int n, const double *M, double *out, cudaStream_t stream, double c0 = 1.0,
                                    const double *B = nullptr, double c1 = 0.0, const double *C = nullptr, double c2 = 0.0);
 cudaError_t launch_pack_tiles(int ts, int count, const int *pose, const double *X, double *out, cudaStream_t stream);
