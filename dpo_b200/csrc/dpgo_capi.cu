@@ -94,6 +94,7 @@ struct dpgo_problem {
   int num_public = 0;
   int *d_public = nullptr;
   int num_edges = 0, num_shared_poses = 0, max_slot = -1;
+  bool G_dirty = true;           // G may hold values that dpgo_agent_build_G does not overwrite
   int *d_pose_ids = nullptr, *d_pose_ptr = nullptr, *d_edge_slot = nullptr, *d_edge_out = nullptr;
   double *d_edge_T = nullptr, *d_edge_om = nullptr;
 
@@ -756,6 +757,7 @@ int dpgo_problem_set_Q_blocks(dpgo_problem_t *p, int64_t nb, const int32_t *brow
 
 int dpgo_problem_set_G_dense(dpgo_problem_t *p, const double *G_host) {
   DPGO_CHECK_HANDLE(p);
+  p->G_dirty = true;
   if (!G_host) {
     DPGO_CUDA(cudaMemsetAsync(p->d_G, 0, p->vec_bytes(), p->stream));
   } else {
@@ -962,6 +964,7 @@ int dpgo_problem_device_X(dpgo_problem_t *p, double **X_dev) {
 int dpgo_problem_device_G(dpgo_problem_t *p, double **G_dev) {
   DPGO_REQUIRE(p && G_dev, DPGO_ERR_INVALID_ARG, "null argument");
   *G_dev = p->d_G;
+  p->G_dirty = true;             // the caller may write G directly
   return DPGO_OK;
 }
 
@@ -1367,6 +1370,7 @@ int dpgo_agent_set_shared_edges(dpgo_problem_t *p, int num_edges, const int32_t 
   free_dev(p->d_pose_ids); free_dev(p->d_pose_ptr); free_dev(p->d_edge_slot); free_dev(p->d_edge_out);
   free_dev(p->d_edge_T); free_dev(p->d_edge_om);
   p->num_edges = num_edges;
+  p->G_dirty = true;
   p->num_shared_poses = (int)pose_ids.size();
   p->max_slot = -1;
   for (int e = 0; e < num_edges; ++e) p->max_slot = std::max(p->max_slot, (int)nbr_slot[e]);
@@ -1392,7 +1396,12 @@ int dpgo_agent_build_G(dpgo_problem_t *p, const double *gathered_dev, int64_t nu
   DPGO_REQUIRE(gathered_dev || p->num_edges == 0, DPGO_ERR_INVALID_ARG, "null gathered buffer");
   DPGO_REQUIRE((int64_t)p->max_slot < num_slots || p->num_edges == 0, DPGO_ERR_INVALID_ARG,
                "a shared edge refers to a slot beyond the gathered buffer (exchange plan / slot table mismatch)");
-  DPGO_CUDA(cudaMemsetAsync(p->d_G, 0, p->vec_bytes(), p->stream));
+  // k_build_G assigns every tile of a pose with shared edges; the other tiles of G are zero and stay zero, so G is cleared
+  // only when something else may have written it (set_G, a new edge table)
+  if (p->G_dirty) {
+    DPGO_CUDA(cudaMemsetAsync(p->d_G, 0, p->vec_bytes(), p->stream));
+    p->G_dirty = false;
+  }
   if (p->num_edges)
     DPGO_CUDA(dpgo::launch_build_G(p->r, p->dh, p->num_shared_poses, p->d_pose_ids, p->d_pose_ptr, p->d_edge_slot,
                                    p->d_edge_out, p->d_edge_T, p->d_edge_om, gathered_dev, p->d_G, p->stream));
