@@ -525,7 +525,7 @@ int build_from_triplets(dpgo_problem *p, std::vector<BlockTriplet> &trip, unsign
   }
   // row groups for the TMA-fed SpMV: consecutive rows, <= SPMV_GROUP_BLOCKS blocks and rows each
   {
-    const int BT = dpgo::SPMV_GROUP_BLOCKS;
+    const int BT = dpgo::spmv_group_blocks();
     std::vector<int2> groups;
     bool ok = true;
     int rr = 0;

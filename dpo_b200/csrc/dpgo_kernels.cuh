@@ -101,6 +101,7 @@ cudaError_t launch_spmv(int r, int dh, int n, const int *rowptr, const int *bcol
 cudaError_t launch_spmv_tma(int r, int dh, int ngroups, const int2 *groups, const int *rowptr, const int *bcol,
                             const double *bval, const double *X, const double *G, double *out, int sms,
                             cudaStream_t stream);
+int spmv_group_blocks();                            // blocks per row group of the TMA-fed SpMV in use
 int optimize_max_grid(int r, int dh, int device);   // co-resident CTA count for the persistent kernel
 int optimize_max_cluster(int r, int dh, int device); // largest single-cluster grid (16, 8 or 0) the kernel can be launched with
 cudaError_t launch_stiefel_project(int r, int dh, int n, const double *M, double *out, cudaStream_t stream, double c0 = 1.0,
