@@ -610,6 +610,7 @@ int dpgo_problem_create(int n, int d, int r, int device, dpgo_problem_t **out) {
   DPGO_REQUIRE(out, DPGO_ERR_INVALID_ARG, "null output handle");
   *out = nullptr;
   DPGO_REQUIRE(n >= 1, DPGO_ERR_INVALID_ARG, "n must be >= 1");
+  DPGO_REQUIRE(n <= 100000000, DPGO_ERR_UNSUPPORTED, "n above 1e8 poses: element offsets are 32-bit in the kernels");
   DPGO_REQUIRE(d == 2 || d == 3, DPGO_ERR_UNSUPPORTED, "d must be 2 or 3");
   DPGO_REQUIRE(r >= d, DPGO_ERR_INVALID_ARG, "r must be >= d (ref: assert(r >= d), src/QuadraticProblem.cpp:19)");
   DPGO_REQUIRE((d == 3 && r <= 5) || (d == 2 && (r <= 3 || r == 5)), DPGO_ERR_UNSUPPORTED,
