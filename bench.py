@@ -543,6 +543,8 @@ def measure_multi(torch, dist, dp, pg, dataset, k, rank, world, local_rank, K, W
         X0d[a] = torch.from_numpy(np.asfortranarray(X0[:, cols]).ravel(order="F").copy()).to(dev)
     cyc = CYCLE * run.ncolours
 
+    launches = [0]
+
     def run_rounds(count, collect=None):
         steps = 0
         with torch.cuda.stream(side):
@@ -551,11 +553,27 @@ def measure_multi(torch, dist, dp, pg, dataset, k, rank, world, local_rank, K, W
                 if c == 0:
                     for a in mine:
                         run.agents[a].mProblem.copy_X_from_device(X0d[a].data_ptr())
+                if run.concurrent:
+                    # the active agents of this rank side by side (one thread-block cluster and one stream each): G rebuild ->
+                    # RTR step -> pack per agent, then the all-gather; a reset of the iterates re-publishes all tiles
+                    if c == 0:
+                        run.exchange(build=False)
+                    act = [a for a in range(run.k) if run.colour[a] == c % run.ncolours]
+                    run._round_concurrent(act)
+                    for a in mine:
+                        if a in act:
+                            steps += 1
+                            launches[0] += 3
+                            if collect is not None:
+                                collect.append((a, run.agents[a].opt.fetch_result()))
+                    continue
                 run.exchange()
+                launches[0] += 2 * len(mine)
                 for a in mine:
                     if run.colour[a] == c % run.ncolours:
                         run.agents[a].opt.optimize_resident_async()
                         steps += 1
+                        launches[0] += 1
                         if collect is not None:
                             collect.append((a, run.agents[a].opt.fetch_result()))
         return steps
@@ -568,7 +586,9 @@ def measure_multi(torch, dist, dp, pg, dataset, k, rank, world, local_rank, K, W
     barrier()
     with torch.cuda.stream(side):
         e0.record()
+    launches[0] = 0
     my_steps = run_rounds(K)
+    timed_launches = launches[0]
     with torch.cuda.stream(side):
         e1.record()
     barrier()
@@ -589,7 +609,10 @@ def measure_multi(torch, dist, dp, pg, dataset, k, rank, world, local_rank, K, W
     ach = alg_per_round / (ms_total / K * 1e-3) / 1e9
     out = {"rounds_per_sec": K / (ms_total * 1e-3), "ms_per_round": ms_total / K, "agent_steps_per_sec": total_steps / (ms_total * 1e-3),
            "colours": run.ncolours, "allgather_bytes_per_rank": run.plan.pmax * RANK_R * dh * 8 * (k // world),
-           "gpu_launches": int(K * 2 * len(mine) + my_steps), "final": {"cost": st.cost, "gradnorm": st.gradnorm},
+           "gpu_launches": int(timed_launches), "final": {"cost": st.cost, "gradnorm": st.gradnorm},
+           "agents_per_gpu": len(mine), "concurrent_agents": bool(run.concurrent),
+           "step_kernel_launch": ("one thread-block cluster of %d CTAs per agent, the round's agents side by side on their own streams"
+                                  if run.concurrent else "cooperative grid of %d CTAs, one agent at a time") % run.agents[mine[0]].mProblem.launch_info()[0],
            "roofline": {"kernel": "k_optimize<5,4> launches of rank 0 (its agents' RTR steps)", "bound": "hbm", "achieved": ach,
                         "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": ach / peak,
                         "algorithmic_bytes_per_round": alg_per_round, "traffic": None,

@@ -57,6 +57,8 @@ SIGNATURES = {
     "dpgo_problem_destroy": (C.c_int, [_vp]),
     "dpgo_problem_set_stream": (C.c_int, [_vp, _vp]),
     "dpgo_problem_sync": (C.c_int, [_vp]),
+    "dpgo_problem_set_launch_mode": (C.c_int, [_vp, C.c_int]),
+    "dpgo_problem_launch_info": (C.c_int, [_vp, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "dpgo_problem_dims": (C.c_int, [_vp, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int),
                                     C.POINTER(C.c_int64)]),
     "dpgo_problem_set_Q_csr": (C.c_int, [_vp, C.c_int, _ip, _ip, _dp, C.c_uint]),
@@ -118,6 +120,8 @@ SIGNATURES = {
     "dpgo_agent_accel_restart_end": (C.c_int, [_vp]),
     "dpgo_agent_pack_public_aux": (C.c_int, [_vp, _vp]),
     "dpgo_optimize_resident_from_aux_async": (C.c_int, [_vp, C.POINTER(OptParams)]),
+    "dpgo_agents_round_async": (C.c_int, [C.POINTER(_vp), C.c_int, C.POINTER(OptParams), _vp, C.c_int64, C.POINTER(_vp), _vp,
+                                          C.c_int]),
     "dpgo_agent_f_rgradnorm_resident": (C.c_int, [_vp, _dp, _dp]),
 }
 

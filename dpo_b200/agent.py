@@ -40,6 +40,7 @@ class PGOAgentParameters:
     verbose: bool = False
     preconditioner: int = capi.PRECOND_SPARSE_EXACT     # B200 extension (reference operator by default)
     device: int = 0
+    cluster: bool = False          # B200 extension: step kernel as one thread-block cluster (several agents per GPU)
 
 
 class PGOAgentState:
@@ -206,7 +207,7 @@ class PGOAgent:
             self.neighborRobotIDs = sorted({int(a) for a in other_r})
         self.n = nn if n is None else int(n)
         self.mProblem = QuadraticProblem(self.n, self.d, self.r, device=self.mParams.device,
-                                         preconditioners=self._precond_set())
+                                         preconditioners=self._precond_set(), cluster=self.mParams.cluster)
         self.constructQMatrix()
         if TInit is not None and np.shape(TInit) == (self.d, (self.d + 1) * self.n):
             self.TLocalInit = np.array(TInit, dtype=float)
@@ -436,7 +437,12 @@ class DistributedPGO:
                  preconditioner: int = capi.PRECOND_SPARSE_EXACT, schedule: str = "greedy",
                  owner: Optional[np.ndarray] = None, X_init: Optional[np.ndarray] = None,
                  rank: Optional[int] = None, world: Optional[int] = None, device: int = 0, dist=None,
-                 acceleration: bool = False, restart_interval: int = 30):
+                 acceleration: bool = False, restart_interval: int = 30, concurrent: Optional[bool] = None):
+        """concurrent: the active agents of a round that share a GPU step side by side (each as one thread-block cluster on
+        its own stream, one C call per round: dpgo_agents_round_async) instead of one after the other as full-grid kernels.
+        None = automatic: on when some round has >= 2 active agents on a rank (greedy / coloured schedules, no
+        acceleration).  The iterates of the two modes agree to rounding, not bitwise (different reduction trees), so
+        comparisons across world sizes must pin the mode."""
         import torch
         self.acceleration, self.restart_interval = bool(acceleration), int(restart_interval)
         self.torch = torch
@@ -458,12 +464,24 @@ class DistributedPGO:
             X_init = pg.fixedStiefelVariable(self.d, r) @ pg.chordalInitialization(self.d, n, edges)
         per_rank = k // self.world
         self.local_ids = list(range(rank * per_rank, (rank + 1) * per_rank)) if self.distributed else list(range(k))
+        if concurrent is None:
+            if schedule == "coloured" and not self.acceleration:
+                # the same decision on every rank: the largest number of same-coloured agents any rank hosts
+                most = max(sum(1 for a in range(q * per_rank, (q + 1) * per_rank) if self.colour[a] == c)
+                           for q in range(k // per_rank) for c in range(self.ncolours))
+                concurrent = most >= 2
+            else:
+                concurrent = False
+        if concurrent and (self.acceleration or schedule == "parallel"):
+            raise ValueError("concurrent rounds are implemented for the greedy and coloured schedules without acceleration")
+        self.concurrent = bool(concurrent)
         self.agents: Dict[int, PGOAgent] = {}
         dh = self.d + 1
         self.dev = torch.device("cuda", device)
         stream = torch.cuda.current_stream(self.dev).cuda_stream
         for a in self.local_ids:
-            prm = PGOAgentParameters(self.d, r, k, algorithm=algorithm, preconditioner=preconditioner, device=device)
+            prm = PGOAgentParameters(self.d, r, k, algorithm=algorithm, preconditioner=preconditioner, device=device,
+                                     cluster=self.concurrent)
             ag = PGOAgent(a, prm)
             ag.mState = PGOAgentState.WAIT_FOR_DATA
             ag.YLift = None
@@ -513,15 +531,32 @@ class DistributedPGO:
         self.stats_all = torch.zeros(4 * k, dtype=torch.float64, device=self.dev)
         self.selected = [0]
         self.round = 0
+        self._main_stream = stream if stream else 1          # 0 = torch's legacy default stream = cudaStreamLegacy (handle 1)
+        self._gathered_current = False       # concurrent mode: `gathered` holds every agent's current public tiles
 
     # -- the exchange: ONE all-gather of the padded public-pose tiles --------------------------------
-    def exchange(self) -> None:
+    def exchange(self, build: bool = True) -> None:
         for a in self.local_ids:
             self.agents[a].pack_public(self.send[a].data_ptr())
         if self.distributed:
             self.dist.all_gather_into_tensor(self.gathered, self.send_all)
-        for a in self.local_ids:
-            self.agents[a].build_G(self.gathered.data_ptr(), self.k * self.plan.pmax)
+        if build:
+            for a in self.local_ids:
+                self.agents[a].build_G(self.gathered.data_ptr(), self.k * self.plan.pmax)
+
+    def _round_concurrent(self, active: List[int]) -> None:
+        """G rebuild -> RTR step -> pack for every active local agent, each on its own stream, with one C call; then the
+        all-gather that publishes the new public tiles.  Asynchronous (no host synchronisation)."""
+        mine = [a for a in self.local_ids if a in active]
+        lib = self.agents[self.local_ids[0]].mProblem._lib
+        if mine:
+            hs = (C.c_void_p * len(mine))(*[self.agents[a].mProblem._h for a in mine])
+            sd = (C.c_void_p * len(mine))(*[C.c_void_p(self.send[a].data_ptr()) for a in mine])
+            capi.check(lib.dpgo_agents_round_async(hs, len(mine), C.byref(self.agents[mine[0]].opt._p),
+                                                   C.c_void_p(self.gathered.data_ptr()), self.k * self.plan.pmax, sd,
+                                                   C.c_void_p(self._main_stream), 0))
+        if self.distributed:
+            self.dist.all_gather_into_tensor(self.gathered, self.send_all)
 
     def _active(self) -> List[int]:
         if self.schedule == "greedy":
@@ -612,15 +647,25 @@ class DistributedPGO:
             if self.schedule == "greedy" and self.plan.tables[self.selected[0]]["neighbors"]:
                 self.selected = [int(np.argmax(per_agent))]
             return RoundStats(cost, gn, active)
-        self.exchange()
         active = self._active()
-        for a in self.local_ids:
-            if a in active:
-                self.agents[a].opt.optimize_resident_async()
-        for a in self.local_ids:
-            if a in active:
-                self.agents[a].lastResult = self.agents[a].opt.fetch_result()
-                self.agents[a].mIterationNumber += 1
+        if self.concurrent:
+            if not self._gathered_current:
+                self.exchange(build=False)
+                self._gathered_current = True
+            self._round_concurrent(active)
+            for a in self.local_ids:
+                if a in active:
+                    self.agents[a].mIterationNumber += 1
+        else:
+            self.exchange()
+            for a in self.local_ids:
+                if a in active:
+                    self.agents[a].opt.optimize_resident_async()
+            for a in self.local_ids:
+                if a in active:
+                    if evaluate:
+                        self.agents[a].lastResult = self.agents[a].opt.fetch_result()
+                    self.agents[a].mIterationNumber += 1
         self.round += 1
         if not evaluate:
             return None
@@ -654,12 +699,20 @@ class DistributedPGO:
             if hx[a] is not self.agents[a].X:
                 hx[a][...] = self.agents[a].X
             self.agents[a].mProblem.upload_X_async(hx[a])
-        self.exchange()
         active = self._active()
-        for a in self.local_ids:
-            if a in active:
-                self.agents[a].opt.optimize_resident_async()
-                self.agents[a].mProblem.download_X_async(hx[a])
+        if self.concurrent:
+            self.exchange(build=False)
+            self._round_concurrent(active)
+            self._gathered_current = True
+            for a in self.local_ids:
+                if a in active:
+                    self.agents[a].mProblem.download_X_async(hx[a])
+        else:
+            self.exchange()
+            for a in self.local_ids:
+                if a in active:
+                    self.agents[a].opt.optimize_resident_async()
+                    self.agents[a].mProblem.download_X_async(hx[a])
         for a in self.local_ids:
             if a in active:
                 self.agents[a].mProblem.sync()

@@ -53,6 +53,8 @@ struct dpgo_problem {
   int device = 0, sms = 0, grid = 0, max_grid = 0, max_cluster = 0;
   bool cluster = false;          // the persistent kernel runs as ONE thread-block cluster (small agents)
   cudaStream_t own_stream = nullptr, stream = nullptr;
+  cudaEvent_t ev_done = nullptr, ev_fork = nullptr;   // fork / join of dpgo_agents_round_async
+  int launch_mode = -1;          // -1: by DPGO_CLUSTER_MAX_POSES (default off), 0: full cooperative grid, 1: one thread-block cluster
   // Q in block-CSR
   int64_t nb = 0;
   bool have_Q = false;
@@ -473,7 +475,8 @@ int build_from_triplets(dpgo_problem *p, std::vector<BlockTriplet> &trip, unsign
   // application) 2.5x slower than 148 SMs and every warp walks several rows per sparse phase.
   static const int cluster_max_poses = [] { const char *e = std::getenv("DPGO_CLUSTER_MAX_POSES"); return e ? std::atoi(e) : 0; }();
   p->cluster = false;
-  if (p->max_cluster >= 8 && n <= cluster_max_poses && !(precond_mask & (1u << DPGO_PRECOND_DENSE_EXACT))) {
+  const bool want_cluster = p->launch_mode == 1 || (p->launch_mode < 0 && n <= cluster_max_poses);
+  if (p->max_cluster >= 8 && want_cluster && !(precond_mask & (1u << DPGO_PRECOND_DENSE_EXACT))) {
     grid = std::max(1, std::min(p->max_cluster, (n + rows_per_pass - 1) / rows_per_pass));
     p->cluster = true;
   }
@@ -674,6 +677,8 @@ int dpgo_problem_destroy(dpgo_problem_t *p) {
   free_dev(p->d_edge_out); free_dev(p->d_edge_T); free_dev(p->d_edge_om);
   free_nd(p);
   if (p->h_result) cudaFreeHost(p->h_result);
+  if (p->ev_done) cudaEventDestroy(p->ev_done);
+  if (p->ev_fork) cudaEventDestroy(p->ev_fork);
   if (p->own_stream) cudaStreamDestroy(p->own_stream);
   delete p;
   return DPGO_OK;
@@ -689,6 +694,21 @@ int dpgo_problem_set_stream(dpgo_problem_t *p, void *cuda_stream) {
 int dpgo_problem_sync(dpgo_problem_t *p) {
   DPGO_CHECK_HANDLE(p);
   DPGO_CUDA(cudaStreamSynchronize(p->stream));
+  return DPGO_OK;
+}
+
+int dpgo_problem_set_launch_mode(dpgo_problem_t *p, int mode) {
+  DPGO_CHECK_HANDLE(p);
+  DPGO_REQUIRE(mode >= -1 && mode <= 1, DPGO_ERR_INVALID_ARG, "launch mode must be -1 (default), 0 (grid) or 1 (cluster)");
+  DPGO_REQUIRE(mode != 1 || p->max_cluster >= 8, DPGO_ERR_UNSUPPORTED, "this device cannot co-schedule a cluster of >= 8 CTAs of the step kernel");
+  p->launch_mode = mode;
+  return DPGO_OK;
+}
+
+int dpgo_problem_launch_info(const dpgo_problem_t *p, int *grid, int *cluster) {
+  DPGO_REQUIRE(p, DPGO_ERR_INVALID_ARG, "null problem handle");
+  if (grid) *grid = p->grid;
+  if (cluster) *cluster = p->cluster ? 1 : 0;
   return DPGO_OK;
 }
 
@@ -1460,6 +1480,53 @@ int dpgo_optimize_resident_from_aux_async(dpgo_problem_t *p, const dpgo_opt_para
   DPGO_ACC_READY(p);
   DPGO_CUDA(cudaMemcpyAsync(p->d_vec[dpgo::V_X0], p->d_acc[0], p->vec_bytes(), cudaMemcpyDeviceToDevice, p->stream));
   return dpgo_optimize_resident_async(p, params);
+}
+
+// One RBCD round of the agents of one GPU, issued with one call.  Every active agent works on its OWN stream:
+//   main stream --fork--> [ G rebuild from the gathered tiles -> RTR step (persistent kernel) -> pack of its public tiles ] --join--> main
+// so agents launched as single thread-block clusters (dpgo_problem_set_launch_mode(p, 1)) share the GPU: up to 8 clusters
+// of 16 CTAs run side by side.  Agents of one colour class are never neighbours, so a pack into the (aliased) gathered
+// buffer cannot race with another active agent's G rebuild; with pack_after_join != 0 (every agent active on the previous
+// round's poses) the packs are issued in a second fork/join instead.
+int dpgo_agents_round_async(dpgo_problem_t *const *agents, int num_active, const dpgo_opt_params_t *params,
+                            const double *gathered_dev, int64_t num_slots, double *const *send_dev, void *main_stream,
+                            int pack_after_join) {
+  DPGO_REQUIRE(num_active >= 0 && (num_active == 0 || (agents && send_dev)) && params, DPGO_ERR_INVALID_ARG, "bad arguments");
+  if (num_active == 0) return DPGO_OK;
+  for (int i = 0; i < num_active; ++i) {
+    DPGO_CHECK_HANDLE(agents[i]);
+    DPGO_REQUIRE(agents[i]->device == agents[0]->device, DPGO_ERR_INVALID_ARG, "the agents of a round must live on one device");
+    DPGO_TRY(check_params(agents[i], params));
+  }
+  cudaStream_t main = main_stream ? (cudaStream_t)main_stream : agents[0]->stream;   // NULL: the stream the first handle is set to
+  dpgo_problem *lead = agents[0];
+  DPGO_CUDA(cudaSetDevice(lead->device));
+  if (!lead->ev_fork) DPGO_CUDA(cudaEventCreateWithFlags(&lead->ev_fork, cudaEventDisableTiming));
+  struct StreamSwap {                      // the agent's kernels go to its own stream for the duration of the call
+    dpgo_problem *p; cudaStream_t saved;
+    explicit StreamSwap(dpgo_problem *q) : p(q), saved(q->stream) { q->stream = q->own_stream; }
+    ~StreamSwap() { p->stream = saved; }
+  };
+  const int passes = pack_after_join ? 2 : 1;
+  for (int pass = 0; pass < passes; ++pass) {
+    DPGO_CUDA(cudaEventRecord(lead->ev_fork, main));
+    for (int i = 0; i < num_active; ++i) {
+      dpgo_problem *p = agents[i];
+      if (!p->ev_done) DPGO_CUDA(cudaEventCreateWithFlags(&p->ev_done, cudaEventDisableTiming));
+      StreamSwap swap(p);
+      if (p->stream != main) DPGO_CUDA(cudaStreamWaitEvent(p->stream, lead->ev_fork, 0));
+      if (pass == 0) {
+        DPGO_TRY(dpgo_agent_build_G(p, gathered_dev, num_slots));
+        DPGO_TRY(dpgo_optimize_resident_async(p, params));
+      }
+      if (pass == passes - 1) DPGO_TRY(dpgo_agent_pack_public(p, send_dev[i]));
+      if (p->stream != main) {
+        DPGO_CUDA(cudaEventRecord(p->ev_done, p->stream));
+        DPGO_CUDA(cudaStreamWaitEvent(main, p->ev_done, 0));
+      }
+    }
+  }
+  return DPGO_OK;
 }
 
 int dpgo_agent_f_rgradnorm_resident(dpgo_problem_t *p, double *f_out, double *norm_out) {

@@ -149,7 +149,8 @@ __global__ void __launch_bounds__(TMA_THREADS, 2)
   constexpr bool KPRED = (DH < 4);                          // k >= DH is summed over: it must contribute zeros
   const bool kok = k < DH;
   const double *Xg = X + (kok ? k * R : 0) + ((a < R) ? a : 0);   // lanes a >= R: row 0 of the tile (result row discarded)
-  const int boff = k * 4 + (lane >> 2);                      // B fragment: column n = lane>>2, row k = lane&3
+  // B fragment: column n = lane>>2, row k = lane&3; columns >= 4 alias columns 0..3 (same 128 bytes: one wavefront)
+  const int boff = k * 4 + ((lane >> 2) & 3);
   const bool st = (a < R) && (k < 2);
   const int ooff = a + 2 * k * R;
   int it = 0;

@@ -31,7 +31,7 @@ class QuadraticProblem:
     """
 
     def __init__(self, n: int, d: int, r: int, device: int = 0,
-                 preconditioners=(PRECOND_BLOCK_JACOBI, PRECOND_SPARSE_EXACT)):
+                 preconditioners=(PRECOND_BLOCK_JACOBI, PRECOND_SPARSE_EXACT), cluster: bool = False):
         self._lib = capi.load_library()
         self.n, self.d, self.r = int(n), int(d), int(r)
         self.N = (self.d + 1) * self.n
@@ -42,6 +42,15 @@ class QuadraticProblem:
         h = C.c_void_p()
         capi.check(self._lib.dpgo_problem_create(self.n, self.d, self.r, device, C.byref(h)))
         self._h = h
+        if cluster:
+            # the step kernel runs as ONE thread-block cluster, so that several small agents share the GPU
+            capi.check(self._lib.dpgo_problem_set_launch_mode(self._h, 1))
+
+    def launch_info(self):
+        """(CTAs of the persistent step kernel, launched as one thread-block cluster?)"""
+        g, c = C.c_int(), C.c_int()
+        capi.check(self._lib.dpgo_problem_launch_info(self._h, C.byref(g), C.byref(c)))
+        return g.value, bool(c.value)
 
     # -- lifetime --------------------------------------------------------------------------
     def close(self) -> None:

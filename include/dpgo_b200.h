@@ -114,6 +114,13 @@ DPGO_API int dpgo_problem_destroy(dpgo_problem_t *p);
 DPGO_API int dpgo_problem_set_stream(dpgo_problem_t *p, void *cuda_stream);
 DPGO_API int dpgo_problem_sync(dpgo_problem_t *p);
 DPGO_API int dpgo_problem_dims(const dpgo_problem_t *p, int *n, int *d, int *r, int64_t *num_blocks);
+/* How the persistent step kernel of this handle is launched; takes effect at the next set_Q (it sizes the row partition
+ * and the block-solve plan).  0: cooperative grid over all SMs (default:
+ * one agent owns the GPU, as in the reference's one-agent-per-machine deployment, examples/MultiRobotExample.cpp:229-334);
+ * 1: ONE thread-block cluster of <= 16 CTAs (non-cooperative launch; hardware cluster barriers end the phases), so that the
+ * steps of several small agents of one colour class run side by side on one GPU (dpgo_agents_round_async); -1: default. */
+DPGO_API int dpgo_problem_set_launch_mode(dpgo_problem_t *p, int mode);
+DPGO_API int dpgo_problem_launch_info(const dpgo_problem_t *p, int *grid, int *cluster);
 
 /* ---- cost matrices ------------------------------------------------------------------- */
 /* ref: QuadraticProblem::setQ(const SparseMatrix&), src/QuadraticProblem.cpp:31-42.
@@ -296,6 +303,15 @@ DPGO_API int dpgo_agent_accel_restart_end(dpgo_problem_t *p);               /* V
 DPGO_API int dpgo_agent_pack_public_aux(dpgo_problem_t *p, double *send_dev);
 /* X = Y, then optimise X in place (ref updateX(true, true): the step starts from the auxiliary iterate) */
 DPGO_API int dpgo_optimize_resident_from_aux_async(dpgo_problem_t *p, const dpgo_opt_params_t *params);
+/* One RBCD round of the active agents of one GPU with one call (ref: the body of the round loop,
+ * examples/MultiRobotExample.cpp:229-334: updateNeighborPoses -> iterate() -> getSharedPoseDict per selected agent).
+ * Every agent works on its own stream between a fork from and a join into main_stream: G rebuild from gathered_dev ->
+ * RTR step -> pack of its public tiles into send_dev[i].  main_stream NULL = the stream the first handle is set to.
+ * pack_after_join != 0 issues the packs in a second fork/join
+ * (needed when neighbouring agents are active in the same round and send_dev aliases gathered_dev). */
+DPGO_API int dpgo_agents_round_async(dpgo_problem_t *const *agents, int num_active, const dpgo_opt_params_t *params,
+                            const double *gathered_dev, int64_t num_slots, double *const *send_dev, void *main_stream,
+                            int pack_after_join);
 /* per-agent Riemannian gradient norm / cost of the resident iterate (greedy selection input) */
 DPGO_API int dpgo_agent_f_rgradnorm_resident(dpgo_problem_t *p, double *f_out, double *norm_out);
 

@@ -11,6 +11,7 @@ sys.path.insert(0, ROOT)
 
 def main():
     ds, k, rounds, out_dir, accel = sys.argv[1], int(sys.argv[2]), int(sys.argv[3]), sys.argv[4], int(sys.argv[5])
+    conc = int(sys.argv[6]) if len(sys.argv) > 6 else 0
     import torch
     import torch.distributed as dist
     from dpo_b200 import posegraph as pg
@@ -20,7 +21,7 @@ def main():
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     edges, n = pg.read_g2o_file(os.path.join(ROOT, "data", ds + ".g2o"))
     run = DistributedPGO(edges, n, k, r=5, schedule="coloured", rank=rank, world=world, device=local, dist=dist,
-                         acceleration=bool(accel))
+                         acceleration=bool(accel), concurrent=bool(conc))
     costs = []
     for _ in range(rounds):
         st = run.step(evaluate=True)

@@ -53,15 +53,18 @@ def test_partition_file_reproduces_golden_trace(ds, iters, data_dir, golden_dir)
     assert np.max(np.abs(np.array(gn) - gold[:, 1]) / gold[:, 1]) <= 5e-8
 
 
-@pytest.mark.parametrize("ds,k,rounds", [("torus3D", 8, 10), ("parking-garage", 4, 8), ("sphere2500", 8, 8)])
-def test_coloured_schedule_matches_oracle(ds, k, rounds, data_dir):
+@pytest.mark.parametrize("ds,k,rounds,conc", [("torus3D", 8, 10, False), ("parking-garage", 4, 8, False), ("sphere2500", 8, 8, False),
+                                              ("torus3D", 8, 10, True), ("parking-garage", 4, 8, True), ("sphere2500", 16, 8, True)])
+def test_coloured_schedule_matches_oracle(ds, k, rounds, conc, data_dir):
     """The schedule the multi-GPU benchmark runs (BASELINE configs 3 and 4 and the sphere2500 scaling workload): k
     agents, coloured RBCD, exact preconditioner -- per-round central cost / gradient norm and the iterates against the
-    oracle's coloured driver (<= 1e-8 relative)."""
+    oracle's coloured driver (<= 1e-8 relative).  conc: the agents of a round one after the other as full-grid
+    cooperative kernels, or side by side as thread-block clusters on their own streams (dpgo_agents_round_async)."""
     from dpo_b200.agent import DistributedPGO
     edges, n = load(ds, data_dir)
     meas, _ = orc.read_g2o(os.path.join(data_dir, ds + ".g2o"))
-    run = DistributedPGO(edges, n, k, r=5, schedule="coloured")
+    run = DistributedPGO(edges, n, k, r=5, schedule="coloured", concurrent=conc)
+    assert run.agents[0].mProblem.launch_info()[1] == conc
     drv = orc.MultiRobotDriver(meas, n, k, r=5, schedule="coloured")
     assert run.colour == drv.colour
     # (parking-garage: ill-conditioned -- kappa ~ 2, tau ~ 1, every tCG solve hits its cap -- rounding differences are amplified)
@@ -89,12 +92,13 @@ def test_final_trajectory_parking_garage(data_dir, golden_dir):
     assert np.abs(T - ref).max() <= 5e-4
 
 
-def test_host_level_round_equals_resident_round(data_dir):
+@pytest.mark.parametrize("conc", [False, True])
+def test_host_level_round_equals_resident_round(conc, data_dir):
     """DistributedPGO.step_host (X from / to pinned host memory every round) == the device-resident rounds, bit for bit;
     step_host_dict (the reference's PoseDict protocol on the host) agrees to rounding."""
     from dpo_b200.agent import DistributedPGO
     edges, n = load("smallGrid3D", data_dir)
-    runs = [DistributedPGO(edges, n, 5, r=5, schedule="coloured") for _ in range(3)]
+    runs = [DistributedPGO(edges, n, 5, r=5, schedule="coloured", concurrent=conc) for _ in range(3)]
     for _ in range(6):
         runs[0].step(evaluate=False)
         runs[1].step_host()

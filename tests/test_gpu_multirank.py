@@ -20,8 +20,11 @@ def _device_count():
     return c.value
 
 
-@pytest.mark.parametrize("ds,k,accel", [("smallGrid3D", 4, 0), ("torus3D", 8, 0), ("smallGrid3D", 4, 1)])
-def test_two_ranks_bit_equal_to_one_process(ds, k, accel, tmp_path, data_dir):
+@pytest.mark.parametrize("ds,k,accel,conc", [("smallGrid3D", 4, 0, 0), ("torus3D", 8, 0, 0), ("smallGrid3D", 4, 1, 0),
+                                              ("torus3D", 8, 0, 1)])
+def test_two_ranks_bit_equal_to_one_process(ds, k, accel, conc, tmp_path, data_dir):
+    """conc = 1: the round's agents of a rank step side by side as thread-block clusters on their own streams
+    (dpgo_agents_round_async); the launch mode is pinned on both sides, the iterates must still be bit-identical."""
     if _device_count() < 2:
         pytest.skip("needs 2 GPUs")
     from dpo_b200 import posegraph as pg
@@ -29,11 +32,11 @@ def test_two_ranks_bit_equal_to_one_process(ds, k, accel, tmp_path, data_dir):
     rounds = 6
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
            "--master-port", "29533", os.path.join(ROOT, "tests", "_multirank_worker.py"), ds, str(k), str(rounds), str(tmp_path),
-           str(accel)]
+           str(accel), str(conc)]
     res = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert res.returncode == 0, res.stderr[-2000:]
     edges, n = pg.read_g2o_file(os.path.join(data_dir, ds + ".g2o"))
-    run = DistributedPGO(edges, n, k, r=5, schedule="coloured", acceleration=bool(accel))
+    run = DistributedPGO(edges, n, k, r=5, schedule="coloured", acceleration=bool(accel), concurrent=bool(conc))
     trace = []
     for _ in range(rounds):
         st = run.step(evaluate=True)
