@@ -54,6 +54,9 @@ struct dpgo_problem {
   bool cluster = false;          // the persistent kernel runs as ONE thread-block cluster (small agents)
   cudaStream_t own_stream = nullptr, stream = nullptr;
   cudaEvent_t ev_done = nullptr, ev_fork = nullptr;   // fork / join of dpgo_agents_round_async
+  uint64_t generation = 0;       // bumped whenever device buffers a captured round refers to may have been replaced
+  struct RoundGraph { std::vector<uint64_t> key; cudaGraphExec_t exec = nullptr; int uses = 0; bool failed = false; };
+  std::vector<RoundGraph> round_graphs;      // CUDA graphs of dpgo_agents_round_async, kept by the first agent of the round
   int launch_mode = -1;          // -1: by DPGO_CLUSTER_MAX_POSES (default off), 0: full cooperative grid, 1: one thread-block cluster
   // Q in block-CSR
   int64_t nb = 0;
@@ -306,6 +309,7 @@ template <class T> int upload_array(const std::vector<T> &h, const T *&d, cudaSt
 }
 
 void free_nd(dpgo_problem *p) {
+  ++p->generation;
   auto fr = [](const void *q) { if (q) cudaFree(const_cast<void *>(q)); };
   fr(p->nd.cta_phase); fr(p->nd.steps); fr(p->nd.gathers); fr(p->nd.jobs); fr(p->nd.epis); fr(p->nd.csrc);
   fr(p->nd.blob); fr(p->nd.TX); fr(p->nd.C);
@@ -366,6 +370,7 @@ int ensure_nd(dpgo_problem *p) {
   DPGO_CUDA(cudaStreamSynchronize(p->stream));
   p->nd.nphases = (int)plan.phases.size();
   p->nd_ready = true;
+  ++p->generation;
   return DPGO_OK;
 }
 
@@ -627,6 +632,10 @@ int dpgo_problem_create(int n, int d, int r, int device, dpgo_problem_t **out) {
   dpgo_problem *p = new (std::nothrow) dpgo_problem();
   if (!p) return fail(DPGO_ERR_ALLOC, "host allocation failed");
   p->n = n; p->d = d; p->r = r; p->dh = d + 1; p->N = (d + 1) * n; p->ts = r * (d + 1);
+  {
+    static uint64_t serial = 0;             // handles are created from one thread at a time (as the rest of this API)
+    p->generation = (++serial) << 24;       // a recycled address never matches the key of a captured round
+  }
   p->device = device;
   auto bail = [&](int code, const std::string &m) { dpgo_problem_destroy(p); return fail(code, m); };
   if (cudaDeviceGetAttribute(&p->sms, cudaDevAttrMultiProcessorCount, device) != cudaSuccess)
@@ -677,6 +686,8 @@ int dpgo_problem_destroy(dpgo_problem_t *p) {
   free_dev(p->d_edge_out); free_dev(p->d_edge_T); free_dev(p->d_edge_om);
   free_nd(p);
   if (p->h_result) cudaFreeHost(p->h_result);
+  for (auto &g : p->round_graphs) if (g.exec) cudaGraphExecDestroy(g.exec);
+  p->round_graphs.clear();
   if (p->ev_done) cudaEventDestroy(p->ev_done);
   if (p->ev_fork) cudaEventDestroy(p->ev_fork);
   if (p->own_stream) cudaStreamDestroy(p->own_stream);
@@ -1342,6 +1353,7 @@ int dpgo_stream_synchronize(int device, void *cuda_stream) {
 // ---- boundary-pose exchange --------------------------------------------------------------------
 int dpgo_agent_set_public_poses(dpgo_problem_t *p, int num_public, const int32_t *public_pose) {
   DPGO_CHECK_HANDLE(p);
+  ++p->generation;
   DPGO_REQUIRE(num_public >= 0 && (num_public == 0 || public_pose), DPGO_ERR_INVALID_ARG, "bad public pose list");
   for (int s = 0; s < num_public; ++s)
     if (public_pose[s] < 0 || public_pose[s] >= p->n) return fail(DPGO_ERR_INVALID_ARG, "public pose index out of range");
@@ -1364,6 +1376,7 @@ int dpgo_agent_pack_public(dpgo_problem_t *p, double *send_dev) {
 int dpgo_agent_set_shared_edges(dpgo_problem_t *p, int num_edges, const int32_t *local_pose, const int32_t *nbr_slot,
                                 const int32_t *outgoing, const double *T, const double *omega) {
   DPGO_CHECK_HANDLE(p);
+  ++p->generation;
   DPGO_REQUIRE(num_edges >= 0 && (num_edges == 0 || (local_pose && nbr_slot && outgoing && T && omega)),
                DPGO_ERR_INVALID_ARG, "bad shared edge arrays");
   const int dh = p->dh;
@@ -1482,26 +1495,10 @@ int dpgo_optimize_resident_from_aux_async(dpgo_problem_t *p, const dpgo_opt_para
   return dpgo_optimize_resident_async(p, params);
 }
 
-// One RBCD round of the agents of one GPU, issued with one call.  Every active agent works on its OWN stream:
-//   main stream --fork--> [ G rebuild from the gathered tiles -> RTR step (persistent kernel) -> pack of its public tiles ] --join--> main
-// so agents launched as single thread-block clusters (dpgo_problem_set_launch_mode(p, 1)) share the GPU: up to 8 clusters
-// of 16 CTAs run side by side.  Agents of one colour class are never neighbours, so a pack into the (aliased) gathered
-// buffer cannot race with another active agent's G rebuild; with pack_after_join != 0 (every agent active on the previous
-// round's poses) the packs are issued in a second fork/join instead.
-int dpgo_agents_round_async(dpgo_problem_t *const *agents, int num_active, const dpgo_opt_params_t *params,
-                            const double *gathered_dev, int64_t num_slots, double *const *send_dev, void *main_stream,
-                            int pack_after_join) {
-  DPGO_REQUIRE(num_active >= 0 && (num_active == 0 || (agents && send_dev)) && params, DPGO_ERR_INVALID_ARG, "bad arguments");
-  if (num_active == 0) return DPGO_OK;
-  for (int i = 0; i < num_active; ++i) {
-    DPGO_CHECK_HANDLE(agents[i]);
-    DPGO_REQUIRE(agents[i]->device == agents[0]->device, DPGO_ERR_INVALID_ARG, "the agents of a round must live on one device");
-    DPGO_TRY(check_params(agents[i], params));
-  }
-  cudaStream_t main = main_stream ? (cudaStream_t)main_stream : agents[0]->stream;   // NULL: the stream the first handle is set to
+static int issue_round(dpgo_problem_t *const *agents, int num_active, const dpgo_opt_params_t *params,
+                       const double *gathered_dev, int64_t num_slots, double *const *send_dev, cudaStream_t main,
+                       int pack_after_join) {
   dpgo_problem *lead = agents[0];
-  DPGO_CUDA(cudaSetDevice(lead->device));
-  if (!lead->ev_fork) DPGO_CUDA(cudaEventCreateWithFlags(&lead->ev_fork, cudaEventDisableTiming));
   struct StreamSwap {                      // the agent's kernels go to its own stream for the duration of the call
     dpgo_problem *p; cudaStream_t saved;
     explicit StreamSwap(dpgo_problem *q) : p(q), saved(q->stream) { q->stream = q->own_stream; }
@@ -1512,7 +1509,6 @@ int dpgo_agents_round_async(dpgo_problem_t *const *agents, int num_active, const
     DPGO_CUDA(cudaEventRecord(lead->ev_fork, main));
     for (int i = 0; i < num_active; ++i) {
       dpgo_problem *p = agents[i];
-      if (!p->ev_done) DPGO_CUDA(cudaEventCreateWithFlags(&p->ev_done, cudaEventDisableTiming));
       StreamSwap swap(p);
       if (p->stream != main) DPGO_CUDA(cudaStreamWaitEvent(p->stream, lead->ev_fork, 0));
       if (pass == 0) {
@@ -1526,6 +1522,99 @@ int dpgo_agents_round_async(dpgo_problem_t *const *agents, int num_active, const
       }
     }
   }
+  return DPGO_OK;
+}
+
+// One RBCD round of the agents of one GPU, issued with one call.  Every active agent works on its OWN stream:
+//   main stream --fork--> [ G rebuild from the gathered tiles -> RTR step (persistent kernel) -> pack of its public tiles ] --join--> main
+// so agents launched as single thread-block clusters (dpgo_problem_set_launch_mode(p, 1)) share the GPU: up to 8 clusters
+// of 16 CTAs run side by side.  Agents of one colour class are never neighbours, so a pack into the (aliased) gathered
+// buffer cannot race with another active agent's G rebuild; with pack_after_join != 0 (every agent active on the previous
+// round's poses) the packs are issued in a second fork/join instead.
+// A round with the same agents, buffers and parameters as an earlier one is replayed as a CUDA graph (the cluster launches
+// are ordinary launches, so the fork/join captures): 1 driver call per round instead of ~7 per agent, which is what
+// bounds 8 agents x ~100 us of GPU work otherwise.  DPGO_ROUND_GRAPH=0 keeps the eager launches.
+int dpgo_agents_round_async(dpgo_problem_t *const *agents, int num_active, const dpgo_opt_params_t *params,
+                            const double *gathered_dev, int64_t num_slots, double *const *send_dev, void *main_stream,
+                            int pack_after_join) {
+  DPGO_REQUIRE(num_active >= 0 && (num_active == 0 || (agents && send_dev)) && params, DPGO_ERR_INVALID_ARG, "bad arguments");
+  if (num_active == 0) return DPGO_OK;
+  bool graphable = true;
+  for (int i = 0; i < num_active; ++i) {
+    DPGO_CHECK_HANDLE(agents[i]);
+    DPGO_REQUIRE(agents[i]->device == agents[0]->device, DPGO_ERR_INVALID_ARG, "the agents of a round must live on one device");
+    DPGO_TRY(check_params(agents[i], params));
+    if (!agents[i]->ev_done) DPGO_CUDA(cudaEventCreateWithFlags(&agents[i]->ev_done, cudaEventDisableTiming));
+    // a cooperative launch does not capture; a pending G clear or an unbuilt factorisation must run eagerly first
+    if (!agents[i]->cluster || agents[i]->G_dirty || agents[i]->d_phase_ns ||
+        ((agents[i]->precond_mask & (1u << DPGO_PRECOND_SPARSE_EXACT)) && !agents[i]->nd_ready))
+      graphable = false;
+  }
+  dpgo_problem *lead = agents[0];
+  cudaStream_t main = main_stream ? (cudaStream_t)main_stream : lead->stream;   // NULL: the stream the first handle is set to
+  DPGO_CUDA(cudaSetDevice(lead->device));
+  if (!lead->ev_fork) DPGO_CUDA(cudaEventCreateWithFlags(&lead->ev_fork, cudaEventDisableTiming));
+  static const bool use_graph = [] { const char *e = std::getenv("DPGO_ROUND_GRAPH"); return !e || std::atoi(e) != 0; }();
+  if (!use_graph || !graphable)
+    return issue_round(agents, num_active, params, gathered_dev, num_slots, send_dev, main, pack_after_join);
+
+  std::vector<uint64_t> key;
+  key.reserve(3 * (size_t)num_active + 8 + sizeof(*params) / 8 + 1);
+  for (int i = 0; i < num_active; ++i) {
+    key.push_back((uint64_t)(uintptr_t)agents[i]);
+    key.push_back(agents[i]->generation);
+    key.push_back((uint64_t)(uintptr_t)send_dev[i]);
+  }
+  key.push_back((uint64_t)(uintptr_t)gathered_dev);
+  key.push_back((uint64_t)num_slots);
+  key.push_back((uint64_t)(uintptr_t)main);
+  key.push_back((uint64_t)pack_after_join);
+  {
+    uint64_t w[(sizeof(*params) + 7) / 8] = {};
+    std::memcpy(w, params, sizeof(*params));
+    key.insert(key.end(), w, w + sizeof(w) / 8);
+  }
+  dpgo_problem::RoundGraph *entry = nullptr;
+  for (auto &g : lead->round_graphs)
+    if (g.key == key) { entry = &g; break; }
+  if (!entry) {
+    if (lead->round_graphs.size() >= 32) {              // e.g. the greedy schedule on many agents: stay eager
+      return issue_round(agents, num_active, params, gathered_dev, num_slots, send_dev, main, pack_after_join);
+    }
+    lead->round_graphs.emplace_back();
+    entry = &lead->round_graphs.back();
+    entry->key = key;
+  }
+  if (entry->exec) {
+    DPGO_CUDA(cudaGraphLaunch(entry->exec, main));
+    for (int i = 0; i < num_active; ++i) agents[i]->async_pending = true;
+    return DPGO_OK;
+  }
+  if (entry->failed || entry->uses++ == 0)                // first time eagerly: warms every lazily created resource
+    return issue_round(agents, num_active, params, gathered_dev, num_slots, send_dev, main, pack_after_join);
+  cudaGraph_t graph = nullptr;
+  if (cudaStreamBeginCapture(main, cudaStreamCaptureModeThreadLocal) != cudaSuccess) {
+    cudaGetLastError();
+    entry->failed = true;
+    return issue_round(agents, num_active, params, gathered_dev, num_slots, send_dev, main, pack_after_join);
+  }
+  const int rc = issue_round(agents, num_active, params, gathered_dev, num_slots, send_dev, main, pack_after_join);
+  const cudaError_t ce = cudaStreamEndCapture(main, &graph);
+  if (rc != DPGO_OK || ce != cudaSuccess || !graph) {
+    cudaGetLastError();
+    if (graph) cudaGraphDestroy(graph);
+    entry->failed = true;
+    return issue_round(agents, num_active, params, gathered_dev, num_slots, send_dev, main, pack_after_join);
+  }
+  const cudaError_t ie = cudaGraphInstantiate(&entry->exec, graph, 0);
+  cudaGraphDestroy(graph);
+  if (ie != cudaSuccess) {
+    cudaGetLastError();
+    entry->exec = nullptr;
+    entry->failed = true;
+    return issue_round(agents, num_active, params, gathered_dev, num_slots, send_dev, main, pack_after_join);
+  }
+  DPGO_CUDA(cudaGraphLaunch(entry->exec, main));
   return DPGO_OK;
 }
 
