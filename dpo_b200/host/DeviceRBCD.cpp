@@ -40,6 +40,8 @@ struct DeviceRBCD::Impl {
   std::vector<std::vector<unsigned>> neighbors;
   dpgo_opt_params_t prm;
   unsigned selected = 0;
+  bool concurrent = false;         // active agents of a GPU side by side (cluster launches, own streams)
+  bool gatheredCurrent = false;    // concurrent mode: the gathered buffers hold every agent's current public tiles
 };
 
 DeviceRBCD::DeviceRBCD(const std::vector<RelativeSEMeasurement> &graph, size_t n, unsigned numAgents, const Matrix &XInit,
@@ -87,6 +89,42 @@ DeviceRBCD::DeviceRBCD(const std::vector<RelativeSEMeasurement> &graph, size_t n
     else priv[a1].push_back(m);
   }
 
+  // ---- agent graph and its greedy colouring in agent order (needed before the agents exist: it decides the launch mode) ----
+  I.neighbors.assign(K, {});
+  for (unsigned a = 0; a < K; ++a) {
+    for (const auto &m : shared[a]) I.neighbors[a].push_back((unsigned)(m.r1 == a ? m.r2 : m.r1));
+    std::sort(I.neighbors[a].begin(), I.neighbors[a].end());
+    I.neighbors[a].erase(std::unique(I.neighbors[a].begin(), I.neighbors[a].end()), I.neighbors[a].end());
+  }
+  mColour.assign(K, 0);
+  {
+    std::vector<int> col(K, -1);
+    for (unsigned a = 0; a < K; ++a) {
+      int c = 0;
+      for (bool clash = true; clash; ) {
+        clash = false;
+        for (unsigned b : I.neighbors[a])
+          if (col[b] == c) { clash = true; ++c; break; }
+      }
+      col[a] = c;
+      mColour[a] = (unsigned)c;
+      mNumColours = std::max(mNumColours, (unsigned)c + 1);
+    }
+  }
+  {
+    unsigned most = 1;
+    if (I.schedule == "coloured")
+      for (unsigned g = 0; g < I.N; ++g)
+        for (unsigned c = 0; c < mNumColours; ++c) {
+          unsigned cnt = 0;
+          for (unsigned a = g * I.perGpu; a < (g + 1) * I.perGpu; ++a) cnt += (mColour[a] == c);
+          most = std::max(most, cnt);
+        }
+    I.concurrent = opt.concurrent < 0 ? (most >= 2) : (opt.concurrent != 0);
+    if (I.concurrent && I.schedule == "parallel")
+      throw std::runtime_error("DeviceRBCD: concurrent rounds are implemented for the greedy and coloured schedules");
+  }
+
   // ---- streams, agents (Q on the agent's GPU), resident iterates ----
   I.stream.assign(I.N, nullptr);
   for (unsigned g = 0; g < I.N; ++g) check(dpgo_stream_create((int)g, &I.stream[g]), "dpgo_stream_create");
@@ -98,6 +136,7 @@ DeviceRBCD::DeviceRBCD(const std::vector<RelativeSEMeasurement> &graph, size_t n
     prm.algorithm = opt.algorithm;
     prm.preconditioner = opt.preconditioner;
     prm.device = (int)(a / I.perGpu);
+    prm.cluster = I.concurrent;
     I.gpuOf[a] = prm.device;
     I.agents.emplace_back(new PGOAgent(a, prm));
     if (a == 0) I.agents[0]->getLiftingMatrix(lift);
@@ -123,7 +162,6 @@ DeviceRBCD::DeviceRBCD(const std::vector<RelativeSEMeasurement> &graph, size_t n
     pub[a].erase(std::unique(pub[a].begin(), pub[a].end()), pub[a].end());
     I.pmax = std::max<unsigned>(I.pmax, (unsigned)pub[a].size());
   }
-  I.neighbors.assign(K, {});
   for (unsigned a = 0; a < K; ++a) {
     const size_t m = shared[a].size();
     std::vector<int32_t> loc(m), slot(m), outg(m);
@@ -144,29 +182,11 @@ DeviceRBCD::DeviceRBCD(const std::vector<RelativeSEMeasurement> &graph, size_t n
       }
       T[e * dh * dh + d * dh + d] = 1.0;
       om[e * dh + d] = s.weight * s.tau;
-      I.neighbors[a].push_back(b);
     }
-    std::sort(I.neighbors[a].begin(), I.neighbors[a].end());
-    I.neighbors[a].erase(std::unique(I.neighbors[a].begin(), I.neighbors[a].end()), I.neighbors[a].end());
     check(dpgo_agent_set_public_poses(I.h[a], (int)pub[a].size(), pub[a].data()), "dpgo_agent_set_public_poses");
     check(dpgo_agent_set_shared_edges(I.h[a], (int)m, loc.data(), slot.data(), outg.data(), T.data(), om.data()),
           "dpgo_agent_set_shared_edges");
   }
-  // greedy colouring of the agent graph in agent order
-  mColour.assign(K, 0);
-  std::vector<int> col(K, -1);
-  for (unsigned a = 0; a < K; ++a) {
-    int c = 0;
-    for (bool clash = true; clash; ) {
-      clash = false;
-      for (unsigned b : I.neighbors[a])
-        if (col[b] == c) { clash = true; ++c; break; }
-    }
-    col[a] = c;
-    mColour[a] = (unsigned)c;
-    mNumColours = std::max(mNumColours, (unsigned)c + 1);
-  }
-
   // ---- exchange buffers and communicators ----
   const size_t slotElems = (size_t)I.pmax * I.ts;
   I.send.assign(I.N, nullptr);
@@ -249,12 +269,47 @@ static std::vector<unsigned> activeSet(const std::string &schedule, unsigned K, 
   return act;
 }
 
+bool DeviceRBCD::concurrent() const { return impl->concurrent; }
+
+// the active agents of every GPU side by side: per GPU ONE call (fork from the GPU's stream, per agent G rebuild -> RTR
+// step -> pack on its own stream, join), then the all-gather that publishes the new public tiles
+void DeviceRBCD::roundConcurrent(const std::vector<unsigned> &active) {
+  Impl &I = *impl;
+  const size_t slotElems = (size_t)I.pmax * I.ts;
+  for (unsigned g = 0; g < I.N; ++g) {
+    std::vector<dpgo_problem *> hs;
+    std::vector<double *> dst;
+    for (unsigned a : active)
+      if ((unsigned)I.gpuOf[a] == g) {
+        hs.push_back(I.h[a]);
+        dst.push_back((I.N == 1) ? I.gathered[g] + a * slotElems : I.send[g] + (a % I.perGpu) * slotElems);
+      }
+    if (hs.empty()) continue;
+    check(dpgo_agents_round_async(hs.data(), (int)hs.size(), &I.prm, I.gathered[g], (int64_t)I.K * I.pmax, dst.data(), I.stream[g], 0),
+          "dpgo_agents_round_async");
+  }
+  if (I.N > 1) {
+    checkNccl(ncclGroupStart(), "ncclGroupStart");
+    for (unsigned g = 0; g < I.N; ++g) {
+      check(dpgo_device_set((int)g), "dpgo_device_set");
+      checkNccl(ncclAllGather(I.send[g], I.gathered[g], I.perGpu * slotElems, ncclDouble, I.comm[g], (cudaStream_t)I.stream[g]),
+                "ncclAllGather");
+    }
+    checkNccl(ncclGroupEnd(), "ncclGroupEnd");
+  }
+}
+
 void DeviceRBCD::runRounds(unsigned rounds) {
   Impl &I = *impl;
   for (unsigned it = 0; it < rounds; ++it) {
-    exchange();
-    for (unsigned a : activeSet(I.schedule, I.K, I.selected, mRound, mColour, mNumColours))
-      check(dpgo_optimize_resident_async(I.h[a], &I.prm), "dpgo_optimize_resident_async");
+    const std::vector<unsigned> act = activeSet(I.schedule, I.K, I.selected, mRound, mColour, mNumColours);
+    if (I.concurrent) {
+      if (!I.gatheredCurrent) { exchange(); I.gatheredCurrent = true; }
+      roundConcurrent(act);
+    } else {
+      exchange();
+      for (unsigned a : act) check(dpgo_optimize_resident_async(I.h[a], &I.prm), "dpgo_optimize_resident_async");
+    }
     ++mRound;
   }
 }
@@ -263,10 +318,15 @@ DeviceRBCDStats DeviceRBCD::step(bool evaluate) {
   Impl &I = *impl;
   DeviceRBCDStats st;
   st.active = activeSet(I.schedule, I.K, I.selected, mRound, mColour, mNumColours);
-  exchange();
-  for (unsigned a : st.active) check(dpgo_optimize_resident_async(I.h[a], &I.prm), "dpgo_optimize_resident_async");
   dpgo_opt_result_t res;
-  for (unsigned a : st.active) check(dpgo_optimize_result(I.h[a], &res), "dpgo_optimize_result");
+  if (I.concurrent) {
+    if (!I.gatheredCurrent) { exchange(); I.gatheredCurrent = true; }
+    roundConcurrent(st.active);
+  } else {
+    exchange();
+    for (unsigned a : st.active) check(dpgo_optimize_resident_async(I.h[a], &I.prm), "dpgo_optimize_resident_async");
+    for (unsigned a : st.active) check(dpgo_optimize_result(I.h[a], &res), "dpgo_optimize_result");
+  }
   ++mRound;
   if (!evaluate) return st;
   exchange();                                          // fresh neighbour poses for the central gradient

@@ -152,6 +152,7 @@ void PGOAgent::setPoseGraph(const std::vector<RelativeSEMeasurement> &inputOdome
   delete mProblemPtr;
   mProblemPtr = new QuadraticProblem(num_poses(), dimension(), relaxation_rank());
   if (mParams.device >= 0) mProblemPtr->setDevice(mParams.device);
+  if (mParams.cluster) mProblemPtr->setClusterLaunch(true);
   mProblemPtr->setPreconditioners(true, mParams.preconditioner == Preconditioner::DenseExact || mParams.preconditioner == Preconditioner::SparseExact,
                                   mParams.preconditioner);
   constructQMatrix();               // Q does not depend on the neighbours

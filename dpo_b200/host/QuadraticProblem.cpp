@@ -39,6 +39,12 @@ QuadraticProblem::~QuadraticProblem() {
 void QuadraticProblem::ensureHandle() const {
   if (mHandle) return;
   check(dpgo_problem_create((int)n, (int)d, (int)r, mDevice, &mHandle), "dpgo_problem_create");
+  if (mCluster) check(dpgo_problem_set_launch_mode(mHandle, 1), "dpgo_problem_set_launch_mode");
+}
+
+void QuadraticProblem::setClusterLaunch(bool on) {
+  if (mHandle) throw std::runtime_error("QuadraticProblem::setClusterLaunch must precede the first use");
+  mCluster = on;
 }
 
 void QuadraticProblem::setDevice(int device) {

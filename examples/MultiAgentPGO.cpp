@@ -109,7 +109,8 @@ int main(int argc, char **argv) {
       run.sync();
       const double bs = std::chrono::duration<double>(std::chrono::steady_clock::now() - b0).count();
       std::cout << "bench: rounds = " << opt.bench << ", rounds/s = " << opt.bench / bs << ", us/round = " << 1e6 * bs / opt.bench
-                << ", all-gather bytes per GPU = " << run.allGatherBytesPerGpu() << std::endl;
+                << ", all-gather bytes per GPU = " << run.allGatherBytesPerGpu()
+                << ", agents of a round " << (run.concurrent() ? "side by side (clusters)" : "one at a time (full grid)") << std::endl;
     }
     return 0;
   }

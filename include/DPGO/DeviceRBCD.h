@@ -13,6 +13,8 @@
 // communicator per GPU (ncclCommInitAll).  Schedules: "greedy" (the reference's: one agent per round, argmax of the block
 // gradient norms -- reproduces the shipped traces), "coloured" (all agents of one colour class of the agent graph per
 // round: same RBCD semantics, concurrent), "parallel" (all agents on the previous round's poses).
+// When a GPU hosts several agents of one colour class, their steps run side by side (one thread-block cluster and one
+// stream per agent, the whole round of a GPU replayed as a CUDA graph): DeviceRBCDOptions::concurrent.
 #ifndef DPGO_DEVICE_RBCD_H
 #define DPGO_DEVICE_RBCD_H
 
@@ -35,6 +37,9 @@ struct DeviceRBCDOptions {
   // pose -> agent (one entry per pose, e.g. from a graph-partition file, ref examples/MultiRobotExample.cpp:76-91);
   // empty: contiguous ranges, the last agent takes the remainder (ref :95-109)
   std::vector<unsigned> owner;
+  // the active agents of a round that share a GPU step side by side, each as one thread-block cluster on its own stream
+  // (dpgo_agents_round_async; greedy / coloured schedules): -1 = when some GPU hosts >= 2 agents of one colour class
+  int concurrent = -1;
 };
 
 struct DeviceRBCDStats {
@@ -57,6 +62,7 @@ class DeviceRBCD {
   void runRounds(unsigned rounds);              // rounds without evaluation (throughput), asynchronous; call sync()
   void sync();
   Matrix assemble();                            // r x (d+1)n iterate on the host
+  bool concurrent() const;
   unsigned numColours() const { return mNumColours; }
   const std::vector<unsigned> &colours() const { return mColour; }
   unsigned round() const { return mRound; }
@@ -64,6 +70,7 @@ class DeviceRBCD {
 
  private:
   struct Impl;
+  void roundConcurrent(const std::vector<unsigned> &active);
   std::unique_ptr<Impl> impl;
   unsigned mNumColours = 1, mRound = 0;
   std::vector<unsigned> mColour;

@@ -57,6 +57,7 @@ struct PGOAgentParameters {
   std::string logDirectory;
   Preconditioner preconditioner = Preconditioner::SparseExact;   // B200 extension
   int device = -1;              // B200 extension: CUDA device of this agent's problem (-1: env DPGO_DEVICE or 0)
+  bool cluster = false;         // B200 extension: step kernel as one thread-block cluster, so that several agents share a GPU
 
   PGOAgentParameters(unsigned dIn, unsigned rIn, unsigned numRobotsIn = 1, ROPTALG algorithmIn = ROPTALG::RTR,
                      bool accel = false, unsigned restartInt = 30, RobustCostType costType = RobustCostType::L2,

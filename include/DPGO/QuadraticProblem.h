@@ -39,6 +39,7 @@ class QuadraticProblem {
 
   // B200 extensions
   void setDevice(int device);                           // before the first setQ; default: env DPGO_DEVICE or 0
+  void setClusterLaunch(bool on);                       // before the first setQ: step kernel as ONE thread-block cluster (dpgo_problem_set_launch_mode)
   void setPreconditioners(bool blockJacobi, bool exact, Preconditioner exactKind = Preconditioner::SparseExact);
   dpgo_problem *handle() const { return mHandle; }
   static int defaultDevice();
@@ -47,6 +48,7 @@ class QuadraticProblem {
   const size_t n = 0, d = 0, r = 0;
   SparseMatrix mQ, mG;
   int mDevice;
+  bool mCluster = false;
   unsigned mPrecondMask;
   mutable dpgo_problem *mHandle = nullptr;
   void ensureHandle() const;

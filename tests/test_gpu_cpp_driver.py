@@ -78,6 +78,17 @@ def test_cpp_resident_runner_reproduces_golden_trace(tmp_path, golden_dir, gpus)
         assert np.max(np.abs(tr[:, 3] - np.array(ot.gradnorm)) / np.array(ot.gradnorm)) <= 1e-7
 
 
+def test_cpp_resident_runner_concurrent_agents_on_one_gpu(tmp_path):
+    """8 agents, coloured schedule, ONE GPU: DeviceRBCD steps the 4 agents of a colour class side by side (thread-block
+    clusters on their own streams, dpgo_agents_round_async, CUDA-graph replay) -- against the oracle's coloured driver."""
+    tr = run_driver(tmp_path, "torus3D", "--robots", "8", "--iters", "10", "--stop", "0", "--resident", "--schedule", "coloured")
+    meas, n = orc.read_g2o(os.path.join(ROOT, "data", "torus3D.g2o"))
+    drv = orc.MultiRobotDriver(meas, n, 8, r=5, schedule="coloured")
+    ot = drv.run(10)
+    assert np.max(np.abs(tr[:, 2] - np.array(ot.cost)) / np.array(ot.cost)) <= 1e-8
+    assert np.max(np.abs(tr[:, 3] - np.array(ot.gradnorm)) / np.array(ot.gradnorm)) <= 1e-7
+
+
 def test_cpp_resident_runner_with_partition_file(tmp_path, golden_dir):
     """--partition: ownership from the reference's graph-partition file through the C++ resident runner."""
     tr = run_driver(tmp_path, "CSAIL", "--robots", "5", "--iters", "50", "--stop", "0", "--resident", "--partition",
