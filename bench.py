@@ -312,7 +312,7 @@ def spmv_roofline(torch, dp, pg, peak_gbs, peak_src, dims=(100, 100, 40), reps=2
     ms = e0.elapsed_time(e1) / reps
     nbytes = prob.spmv_algorithmic_bytes(False)
     ach = nbytes / (ms * 1e-3) / 1e9
-    res = {"kernel": "k_spmv_tma<5,4,192> (Out = X Q; bulk-TMA producer, DMMA consumers)", "workload": f"synthetic grid {dims[0]}x{dims[1]}x{dims[2]} = {n} poses, "
+    res = {"kernel": "k_spmv_tma<5,4,192> (Out = X Q; bulk-TMA producer, predicate-light DMMA consumers)", "workload": f"synthetic grid {dims[0]}x{dims[1]}x{dims[2]} = {n} poses, "
            f"{len(edges)} edges, r={RANK_R}, nb={prob.num_blocks()} blocks", "bound": "hbm", "achieved": ach,
            "peak": peak_gbs, "peak_source": peak_src, "unit": "GB/s", "frac": ach / peak_gbs,
            "algorithmic_bytes_per_launch": nbytes, "us_per_launch": ms * 1e3, "launches_timed": reps,
