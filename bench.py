@@ -13,8 +13,8 @@ tolerance is reached, so every timed step does full work.
  N = 1 : sphere2500 as ONE agent (r = 5).   value = steps/s with the iterate resident in HBM;
          e2e   = the same through QuadraticOptimizer.optimize() with pinned host buffers (H2D + D2H per step).
  N > 1 : sphere2500 split contiguously into 8 agents -- the SAME 8-agent problem at every GPU count, 8/N agents per
-         GPU, identical iterates; every round = pack public poses -> one NCCL all-gather -> device-side G rebuild ->
-         the agents of the round's colour class take one RTR step.  value = RBCD rounds/s ("strong": fixed work,
+         GPU; every round = pack public poses -> one NCCL all-gather -> device-side G rebuild -> the agents of the
+         round's colour class take one RTR step (side by side as thread-block clusters while a GPU hosts >= 2 of them).  value = RBCD rounds/s ("strong": fixed work,
          more GPUs); the reference arm runs the same 8-agent coloured RBCD on the host cores.  The N = 1 line carries
          the 1-GPU point of that curve under "multi_agent_1gpu"; torus3D (8 agents) is measured alongside.
 """
@@ -474,7 +474,8 @@ def run_gpu_arm(args):
             line["multi_agent_1gpu"] = {}
             for ds in (DATASET, "torus3D"):
                 m = measure_multi(torch, None, dp, pg, ds, MULTI_AGENTS, 0, 1, local_rank, max(K, 48), W, peak, peak_src, with_e2e=False)
-                line["multi_agent_1gpu"][ds] = {k2: m[k2] for k2 in ("rounds_per_sec", "ms_per_round", "agent_steps_per_sec", "colours", "final")}
+                line["multi_agent_1gpu"][ds] = {k2: m[k2] for k2 in ("rounds_per_sec", "ms_per_round", "agent_steps_per_sec", "colours", "final",
+                                                                     "concurrent_agents", "step_kernel_launch")}
         if not args.no_spmv:
             line["roofline_spmv"] = spmv_roofline(torch, dp, pg, peak, peak_src)
             if not args.no_sweep:
@@ -503,13 +504,15 @@ def run_gpu_arm(args):
             line.update({
                 "value": res["rounds_per_sec"], "ms_per_step": res["ms_per_round"], "steps": K,
                 "config": dict(multi_config(DATASET, MULTI_AGENTS, res["colours"], f"{MULTI_AGENTS // world} agent(s) per GPU, one process per GPU"),
-                               rounds=K, launch_mode="eager launches on a side stream", parallelism=f"agents{MULTI_AGENTS}/gpus{world}",
+                               rounds=K, launch_mode=res["step_kernel_launch"] + ("; per rank one dpgo_agents_round_async call per round, replayed as a CUDA graph"
+                                                                                 if res["concurrent_agents"] else "; eager launches on a side stream"),
+                               concurrent_agents=res["concurrent_agents"], parallelism=f"agents{MULTI_AGENTS}/gpus{world}",
                                allgather_bytes_per_rank=res["allgather_bytes_per_rank"]),
                 "rounds_per_sec": res["rounds_per_sec"], "agent_steps_per_sec": res["agent_steps_per_sec"],
                 "e2e": res["e2e"], "gpu_launches": res["gpu_launches"], "clocks": clocks, "roofline": res["roofline"],
                 "final": res["final"],
                 "torus3D": {k2: tor[k2] for k2 in ("rounds_per_sec", "ms_per_round", "agent_steps_per_sec", "colours", "final",
-                                                    "roofline", "allgather_bytes_per_rank")},
+                                                    "roofline", "allgather_bytes_per_rank", "concurrent_agents", "step_kernel_launch")},
             })
             print(json.dumps(line))
         dist.destroy_process_group()
