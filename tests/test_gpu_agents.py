@@ -63,18 +63,24 @@ def test_coloured_schedule_matches_oracle(ds, k, rounds, conc, data_dir):
     from dpo_b200.agent import DistributedPGO
     edges, n = load(ds, data_dir)
     meas, _ = orc.read_g2o(os.path.join(data_dir, ds + ".g2o"))
-    run = DistributedPGO(edges, n, k, r=5, schedule="coloured", concurrent=conc)
-    assert run.agents[0].mProblem.launch_info()[1] == conc
-    drv = orc.MultiRobotDriver(meas, n, k, r=5, schedule="coloured")
-    assert run.colour == drv.colour
-    # (parking-garage: ill-conditioned -- kappa ~ 2, tau ~ 1, every tCG solve hits its cap -- rounding differences are amplified)
-    ctol, gtol, xtol = (1e-7, 1e-5, 1e-5) if ds == "parking-garage" else (1e-8, 1e-7, 1e-8)
-    for _ in range(rounds):
-        st = run.step()
-        cost, gn = drv.step()
-        assert abs(st.cost - cost) <= ctol * abs(cost)
-        assert abs(st.gradnorm - gn) <= gtol * gn
-    Xg, Xo = run.assemble(), drv.assemble()
+    import contextlib
+    import torch
+    # side by side: on a side stream, so that the repeated rounds are replayed as CUDA graphs (the legacy default stream
+    # cannot be captured; there the call falls back to eager launches)
+    ctx = torch.cuda.stream(torch.cuda.Stream()) if conc else contextlib.nullcontext()
+    with ctx:
+        run = DistributedPGO(edges, n, k, r=5, schedule="coloured", concurrent=conc)
+        assert run.agents[0].mProblem.launch_info()[1] == conc
+        drv = orc.MultiRobotDriver(meas, n, k, r=5, schedule="coloured")
+        assert run.colour == drv.colour
+        # (parking-garage: ill-conditioned -- kappa ~ 2, tau ~ 1, every tCG solve hits its cap -- rounding differences are amplified)
+        ctol, gtol, xtol = (1e-7, 1e-5, 1e-5) if ds == "parking-garage" else (1e-8, 1e-7, 1e-8)
+        for _ in range(rounds):
+            st = run.step()
+            cost, gn = drv.step()
+            assert abs(st.cost - cost) <= ctol * abs(cost)
+            assert abs(st.gradnorm - gn) <= gtol * gn
+        Xg, Xo = run.assemble(), drv.assemble()
     assert np.linalg.norm(Xg - Xo) <= xtol * np.linalg.norm(Xo)
 
 
