@@ -1559,6 +1559,7 @@ int dpgo_agents_round_async(dpgo_problem_t *const *agents, int num_active, const
   DPGO_CUDA(cudaSetDevice(lead->device));
   if (!lead->ev_fork) DPGO_CUDA(cudaEventCreateWithFlags(&lead->ev_fork, cudaEventDisableTiming));
   static const bool use_graph = [] { const char *e = std::getenv("DPGO_ROUND_GRAPH"); return !e || std::atoi(e) != 0; }();
+  if (main == cudaStreamLegacy || main == nullptr) graphable = false;   // the legacy default stream cannot be captured
   if (!use_graph || !graphable)
     return issue_round(agents, num_active, params, gathered_dev, num_slots, send_dev, main, pack_after_join);
 
