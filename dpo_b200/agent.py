@@ -422,6 +422,19 @@ class RoundStats:
     selected: List[int]
 
 
+def auto_concurrent(colour: Sequence[int], k: int, world: int, schedule: str, acceleration: bool) -> bool:
+    """Default launch mode of a k-agent run over `world` ranks (contiguous blocks of k/world agents per rank): the agents of
+    a round step side by side (thread-block clusters, dpgo_agents_round_async) when some rank hosts >= 2 agents of one
+    colour class under the coloured schedule.  A pure function of the global plan, so every rank decides alike."""
+    if schedule != "coloured" or acceleration:
+        return False
+    per_rank = k // max(world, 1)
+    ncol = max(colour) + 1
+    most = max(sum(1 for a in range(q * per_rank, (q + 1) * per_rank) if colour[a] == c)
+               for q in range(max(world, 1)) for c in range(ncol))
+    return most >= 2
+
+
 class DistributedPGO:
     """One agent per rank (torch.distributed) or all agents in one process (single-GPU simulation).
 
@@ -465,13 +478,7 @@ class DistributedPGO:
         per_rank = k // self.world
         self.local_ids = list(range(rank * per_rank, (rank + 1) * per_rank)) if self.distributed else list(range(k))
         if concurrent is None:
-            if schedule == "coloured" and not self.acceleration:
-                # the same decision on every rank: the largest number of same-coloured agents any rank hosts
-                most = max(sum(1 for a in range(q * per_rank, (q + 1) * per_rank) if self.colour[a] == c)
-                           for q in range(k // per_rank) for c in range(self.ncolours))
-                concurrent = most >= 2
-            else:
-                concurrent = False
+            concurrent = auto_concurrent(self.colour, k, self.world, schedule, self.acceleration)
         if concurrent and (self.acceleration or schedule == "parallel"):
             raise ValueError("concurrent rounds are implemented for the greedy and coloured schedules without acceleration")
         self.concurrent = bool(concurrent)

@@ -140,3 +140,19 @@ def test_partition_and_colouring():
     for a in range(5):
         for b in plan.tables[a]["neighbors"]:
             assert col[a] != col[b]
+
+
+def test_auto_concurrent_launch_mode():
+    """The default launch mode of the device runner is a pure function of the global plan (every rank decides alike):
+    agents side by side only under the coloured schedule when a rank hosts >= 2 agents of one colour class."""
+    sys.path.insert(0, ROOT)
+    from dpo_b200.agent import auto_concurrent
+    chain16 = [a % 2 for a in range(16)]                     # the bench workload: 16 agents in a chain, 2 colours
+    assert auto_concurrent(chain16, 16, 1, "coloured", False)            # 8 per colour on one GPU
+    assert auto_concurrent(chain16, 16, 2, "coloured", False)            # 4 per colour and rank
+    assert auto_concurrent(chain16, 16, 4, "coloured", False)            # 2 per colour and rank
+    assert not auto_concurrent(chain16, 16, 8, "coloured", False)        # one of each colour per rank: full-grid kernels
+    assert not auto_concurrent(chain16, 16, 1, "greedy", False)
+    assert not auto_concurrent(chain16, 16, 1, "parallel", False)
+    assert not auto_concurrent(chain16, 16, 1, "coloured", True)         # accelerated rounds keep the sequential path
+    assert not auto_concurrent([0, 1, 2], 3, 1, "coloured", False)       # a triangle of agents: one per colour
