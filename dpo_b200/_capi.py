@@ -122,6 +122,7 @@ SIGNATURES = {
     "dpgo_optimize_resident_from_aux_async": (C.c_int, [_vp, C.POINTER(OptParams)]),
     "dpgo_agents_round_async": (C.c_int, [C.POINTER(_vp), C.c_int, C.POINTER(OptParams), _vp, C.c_int64, C.POINTER(_vp), _vp,
                                           C.c_int]),
+    "dpgo_agents_host_io_async": (C.c_int, [C.POINTER(_vp), C.c_int, C.POINTER(_vp), C.POINTER(_vp), C.c_int, _vp]),
     "dpgo_agent_f_rgradnorm_resident": (C.c_int, [_vp, _dp, _dp]),
 }
 

@@ -551,7 +551,7 @@ class DistributedPGO:
             for a in self.local_ids:
                 self.agents[a].build_G(self.gathered.data_ptr(), self.k * self.plan.pmax)
 
-    def _round_concurrent(self, active: List[int]) -> None:
+    def _round_concurrent(self, active: List[int], publish: bool = True) -> None:
         """G rebuild -> RTR step -> pack for every active local agent, each on its own stream, with one C call; then the
         all-gather that publishes the new public tiles.  Asynchronous (no host synchronisation)."""
         mine = [a for a in self.local_ids if a in active]
@@ -562,7 +562,7 @@ class DistributedPGO:
             capi.check(lib.dpgo_agents_round_async(hs, len(mine), C.byref(self.agents[mine[0]].opt._p),
                                                    C.c_void_p(self.gathered.data_ptr()), self.k * self.plan.pmax, sd,
                                                    C.c_void_p(self._main_stream), 0))
-        if self.distributed:
+        if self.distributed and publish:
             self.dist.all_gather_into_tensor(self.gathered, self.send_all)
 
     def _active(self) -> List[int]:
@@ -705,15 +705,39 @@ class DistributedPGO:
         for a in self.local_ids:
             if hx[a] is not self.agents[a].X:
                 hx[a][...] = self.agents[a].X
-            self.agents[a].mProblem.upload_X_async(hx[a])
+            if not self.concurrent:
+                self.agents[a].mProblem.upload_X_async(hx[a])
         active = self._active()
         if self.concurrent:
-            self.exchange(build=False)
-            self._round_concurrent(active)
-            self._gathered_current = True
-            for a in self.local_ids:
-                if a in active:
-                    self.agents[a].mProblem.download_X_async(hx[a])
+            # one call per direction for the host boundary (uploads + packs / downloads, replayed as CUDA graphs), one
+            # for the round, one synchronisation
+            mine = [a for a in self.local_ids if a in active]
+            lib = self.agents[self.local_ids[0]].mProblem._lib
+            if not hasattr(self, "_io"):
+                self._io = {}
+            def arrays(ids, with_send):
+                key = (tuple(ids), with_send)
+                if key not in self._io:
+                    hs = (C.c_void_p * len(ids))(*[self.agents[a].mProblem._h for a in ids])
+                    hp = (C.c_void_p * len(ids))(*[C.c_void_p(self._hx_keep[a].data_ptr()) for a in ids])
+                    sd = (C.c_void_p * len(ids))(*[C.c_void_p(self.send[a].data_ptr()) for a in ids]) if with_send else None
+                    self._io[key] = (hs, hp, sd)
+                return self._io[key]
+            hs, hp, sd = arrays(self.local_ids, True)
+            capi.check(lib.dpgo_agents_host_io_async(hs, len(self.local_ids), hp, sd, 0, C.c_void_p(self._main_stream)))
+            if self.distributed:
+                self.dist.all_gather_into_tensor(self.gathered, self.send_all)
+            self._round_concurrent(active, publish=False)    # the next host round re-publishes every agent's tiles
+            self._gathered_current = False
+            if mine:
+                hs, hp, _ = arrays(mine, False)
+                capi.check(lib.dpgo_agents_host_io_async(hs, len(mine), hp, None, 1, C.c_void_p(self._main_stream)))
+                self.agents[mine[0]].mProblem.sync()
+            for a in mine:
+                self.agents[a].X = hx[a]
+                self.agents[a].mIterationNumber += 1
+            self.round += 1
+            return
         else:
             self.exchange()
             for a in self.local_ids:

@@ -1499,21 +1499,74 @@ int dpgo_optimize_resident_from_aux_async(dpgo_problem_t *p, const dpgo_opt_para
   return dpgo_optimize_resident_async(p, params);
 }
 
+}  // extern "C"
+
+namespace {
+
+struct StreamSwap {                        // the handle's work goes to another stream for the duration of a call
+  dpgo_problem *p; cudaStream_t saved;
+  StreamSwap(dpgo_problem *q, cudaStream_t to) : p(q), saved(q->stream) { q->stream = to; }
+  ~StreamSwap() { p->stream = saved; }
+};
+
+// Replay a repeated multi-launch sequence as a CUDA graph.  The graphs live with `lead` (the first agent of the call),
+// keyed by everything the captured launches depend on.  First use: eager (warms every lazily created resource);
+// second use: captured while it is issued, instantiated and launched; later: one cudaGraphLaunch.
+template <class Issue> int replay_or_issue(dpgo_problem *lead, const std::vector<uint64_t> &key, cudaStream_t main, Issue issue) {
+  dpgo_problem::RoundGraph *entry = nullptr;
+  for (auto &g : lead->round_graphs)
+    if (g.key == key) { entry = &g; break; }
+  if (!entry) {
+    if (lead->round_graphs.size() >= 48) return issue();      // e.g. the greedy schedule on many agents: stay eager
+    lead->round_graphs.emplace_back();
+    entry = &lead->round_graphs.back();
+    entry->key = key;
+  }
+  if (entry->exec) {
+    DPGO_CUDA(cudaGraphLaunch(entry->exec, main));
+    return DPGO_OK;
+  }
+  if (entry->failed || entry->uses++ == 0) return issue();
+  cudaGraph_t graph = nullptr;
+  if (cudaStreamBeginCapture(main, cudaStreamCaptureModeThreadLocal) != cudaSuccess) {
+    cudaGetLastError();
+    entry->failed = true;
+    return issue();
+  }
+  const int rc = issue();
+  const cudaError_t ce = cudaStreamEndCapture(main, &graph);
+  if (rc != DPGO_OK || ce != cudaSuccess || !graph) {
+    cudaGetLastError();
+    if (graph) cudaGraphDestroy(graph);
+    entry->failed = true;
+    return issue();
+  }
+  const cudaError_t ie = cudaGraphInstantiate(&entry->exec, graph, 0);
+  cudaGraphDestroy(graph);
+  if (ie != cudaSuccess) {
+    cudaGetLastError();
+    entry->exec = nullptr;
+    entry->failed = true;
+    return issue();
+  }
+  DPGO_CUDA(cudaGraphLaunch(entry->exec, main));
+  return DPGO_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
 static int issue_round(dpgo_problem_t *const *agents, int num_active, const dpgo_opt_params_t *params,
                        const double *gathered_dev, int64_t num_slots, double *const *send_dev, cudaStream_t main,
                        int pack_after_join) {
   dpgo_problem *lead = agents[0];
-  struct StreamSwap {                      // the agent's kernels go to its own stream for the duration of the call
-    dpgo_problem *p; cudaStream_t saved;
-    explicit StreamSwap(dpgo_problem *q) : p(q), saved(q->stream) { q->stream = q->own_stream; }
-    ~StreamSwap() { p->stream = saved; }
-  };
   const int passes = pack_after_join ? 2 : 1;
   for (int pass = 0; pass < passes; ++pass) {
     DPGO_CUDA(cudaEventRecord(lead->ev_fork, main));
     for (int i = 0; i < num_active; ++i) {
       dpgo_problem *p = agents[i];
-      StreamSwap swap(p);
+      StreamSwap swap(p, p->own_stream);      // the agent's kernels go to its own stream
       if (p->stream != main) DPGO_CUDA(cudaStreamWaitEvent(p->stream, lead->ev_fork, 0));
       if (pass == 0) {
         DPGO_TRY(dpgo_agent_build_G(p, gathered_dev, num_slots));
@@ -1579,48 +1632,64 @@ int dpgo_agents_round_async(dpgo_problem_t *const *agents, int num_active, const
     std::memcpy(w, params, sizeof(*params));
     key.insert(key.end(), w, w + sizeof(w) / 8);
   }
-  dpgo_problem::RoundGraph *entry = nullptr;
-  for (auto &g : lead->round_graphs)
-    if (g.key == key) { entry = &g; break; }
-  if (!entry) {
-    if (lead->round_graphs.size() >= 32) {              // e.g. the greedy schedule on many agents: stay eager
-      return issue_round(agents, num_active, params, gathered_dev, num_slots, send_dev, main, pack_after_join);
+  auto issue = [&]() { return issue_round(agents, num_active, params, gathered_dev, num_slots, send_dev, main, pack_after_join); };
+  return replay_or_issue(lead, key, main, issue);
+}
+
+// The host boundary of a round with one call per direction (the end-to-end path of DistributedPGO.step_host):
+//   direction 0: X of every listed agent from (pinned) host memory, then its public tiles packed into send_dev[i]
+//   direction 1: X of every listed agent back to host memory
+// all on `stream`; a repeated call (same agents, buffers, stream) is replayed as a CUDA graph of memcpy / kernel nodes.
+int dpgo_agents_host_io_async(dpgo_problem_t *const *agents, int count, double *const *X_host, double *const *send_dev,
+                              int direction, void *stream) {
+  DPGO_REQUIRE(count >= 0 && (count == 0 || (agents && X_host)) && (direction == 0 || direction == 1), DPGO_ERR_INVALID_ARG,
+               "bad arguments");
+  if (count == 0) return DPGO_OK;
+  for (int i = 0; i < count; ++i) {
+    DPGO_CHECK_HANDLE(agents[i]);
+    DPGO_REQUIRE(X_host[i], DPGO_ERR_INVALID_ARG, "null host buffer");
+    DPGO_REQUIRE(agents[i]->device == agents[0]->device, DPGO_ERR_INVALID_ARG, "the agents of a call must live on one device");
+  }
+  dpgo_problem *lead = agents[0];
+  cudaStream_t main = stream ? (cudaStream_t)stream : lead->stream;
+  DPGO_CUDA(cudaSetDevice(lead->device));
+  if (!lead->ev_fork) DPGO_CUDA(cudaEventCreateWithFlags(&lead->ev_fork, cudaEventDisableTiming));
+  for (int i = 0; i < count; ++i)
+    if (!agents[i]->ev_done) DPGO_CUDA(cudaEventCreateWithFlags(&agents[i]->ev_done, cudaEventDisableTiming));
+  auto issue = [&]() -> int {
+    // every agent's copy (+ pack) on its own stream between a fork from and a join into `main`: the copies of different
+    // agents overlap each other and the packs
+    DPGO_CUDA(cudaEventRecord(lead->ev_fork, main));
+    for (int i = 0; i < count; ++i) {
+      dpgo_problem *p = agents[i];
+      StreamSwap swap(p, p->own_stream);
+      if (p->stream != main) DPGO_CUDA(cudaStreamWaitEvent(p->stream, lead->ev_fork, 0));
+      if (direction == 0) {
+        DPGO_TRY(upload_vec(p, dpgo::V_X0, X_host[i]));
+        if (send_dev && send_dev[i]) DPGO_TRY(dpgo_agent_pack_public(p, send_dev[i]));
+      } else {
+        DPGO_TRY(download_vec(p, dpgo::V_X0, X_host[i]));
+      }
+      if (p->stream != main) {
+        DPGO_CUDA(cudaEventRecord(p->ev_done, p->stream));
+        DPGO_CUDA(cudaStreamWaitEvent(main, p->ev_done, 0));
+      }
     }
-    lead->round_graphs.emplace_back();
-    entry = &lead->round_graphs.back();
-    entry->key = key;
-  }
-  if (entry->exec) {
-    DPGO_CUDA(cudaGraphLaunch(entry->exec, main));
-    for (int i = 0; i < num_active; ++i) agents[i]->async_pending = true;
     return DPGO_OK;
+  };
+  static const bool use_graph = [] { const char *e = std::getenv("DPGO_ROUND_GRAPH"); return !e || std::atoi(e) != 0; }();
+  if (!use_graph || main == cudaStreamLegacy || main == nullptr) return issue();
+  std::vector<uint64_t> key;
+  key.reserve(3 * (size_t)count + 4);
+  key.push_back(0x696f0000ull + (uint64_t)direction);       // "io": never equal to a round key (those start with a pointer)
+  for (int i = 0; i < count; ++i) {
+    key.push_back((uint64_t)(uintptr_t)agents[i]);
+    key.push_back(agents[i]->generation);
+    key.push_back((uint64_t)(uintptr_t)X_host[i]);
+    key.push_back((uint64_t)(uintptr_t)((send_dev && direction == 0) ? send_dev[i] : nullptr));
   }
-  if (entry->failed || entry->uses++ == 0)                // first time eagerly: warms every lazily created resource
-    return issue_round(agents, num_active, params, gathered_dev, num_slots, send_dev, main, pack_after_join);
-  cudaGraph_t graph = nullptr;
-  if (cudaStreamBeginCapture(main, cudaStreamCaptureModeThreadLocal) != cudaSuccess) {
-    cudaGetLastError();
-    entry->failed = true;
-    return issue_round(agents, num_active, params, gathered_dev, num_slots, send_dev, main, pack_after_join);
-  }
-  const int rc = issue_round(agents, num_active, params, gathered_dev, num_slots, send_dev, main, pack_after_join);
-  const cudaError_t ce = cudaStreamEndCapture(main, &graph);
-  if (rc != DPGO_OK || ce != cudaSuccess || !graph) {
-    cudaGetLastError();
-    if (graph) cudaGraphDestroy(graph);
-    entry->failed = true;
-    return issue_round(agents, num_active, params, gathered_dev, num_slots, send_dev, main, pack_after_join);
-  }
-  const cudaError_t ie = cudaGraphInstantiate(&entry->exec, graph, 0);
-  cudaGraphDestroy(graph);
-  if (ie != cudaSuccess) {
-    cudaGetLastError();
-    entry->exec = nullptr;
-    entry->failed = true;
-    return issue_round(agents, num_active, params, gathered_dev, num_slots, send_dev, main, pack_after_join);
-  }
-  DPGO_CUDA(cudaGraphLaunch(entry->exec, main));
-  return DPGO_OK;
+  key.push_back((uint64_t)(uintptr_t)main);
+  return replay_or_issue(lead, key, main, issue);
 }
 
 int dpgo_agent_f_rgradnorm_resident(dpgo_problem_t *p, double *f_out, double *norm_out) {

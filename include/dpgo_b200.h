@@ -312,6 +312,12 @@ DPGO_API int dpgo_optimize_resident_from_aux_async(dpgo_problem_t *p, const dpgo
 DPGO_API int dpgo_agents_round_async(dpgo_problem_t *const *agents, int num_active, const dpgo_opt_params_t *params,
                             const double *gathered_dev, int64_t num_slots, double *const *send_dev, void *main_stream,
                             int pack_after_join);
+/* The host boundary of a round with one call per direction (ref: the host matrices PGOAgent::setX / getX move,
+ * src/PGOAgent.cpp:66-93): direction 0 = X of every listed agent from (pinned) host memory, then its public tiles packed
+ * into send_dev[i] (send_dev may be NULL); direction 1 = X back to host memory.  Asynchronous on `stream` (NULL: the
+ * stream the first handle is set to); a repeated call is replayed as a CUDA graph. */
+DPGO_API int dpgo_agents_host_io_async(dpgo_problem_t *const *agents, int count, double *const *X_host,
+                              double *const *send_dev, int direction, void *stream);
 /* per-agent Riemannian gradient norm / cost of the resident iterate (greedy selection input) */
 DPGO_API int dpgo_agent_f_rgradnorm_resident(dpgo_problem_t *p, double *f_out, double *norm_out);
 
