@@ -653,7 +653,9 @@ def measure_multi(torch, dist, dp, pg, dataset, k, rank, world, local_rank, K, W
         h2d, d2h = run.host_bytes_per_step()
         out["e2e"] = {"value": KE / float(te[0]), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "rounds": KE,
                       "api": "DistributedPGO.step_host(): per round every local agent's X from pinned host memory (H2D), device-side "
-                             "exchange (pack -> all-gather -> G rebuild), RTR step of the active agents, their X back to the host (D2H)"}
+                             "exchange (pack -> all-gather -> G rebuild), RTR step of the active agents, their X back to the host (D2H)"
+                             + ("; 3 C calls per round (dpgo_agents_host_io_async x2, dpgo_agents_round_async), each replayed as a CUDA graph"
+                                if run.concurrent else "")}
     for a in mine:
         run.agents[a].mProblem.close()
     return out
