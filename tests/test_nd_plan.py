@@ -45,7 +45,9 @@ def relerr(a, b):
 @pytest.mark.parametrize("ds,r,grid,cuts", [("tinyGrid3D", 3, 148, -1), ("smallGrid3D", 5, 148, -1), ("smallGrid3D", 5, 8, 2),
                                             ("CSAIL", 3, 148, -1), ("CSAIL", 2, 20, 3), ("sphere2500", 5, 148, -1),
                                             ("sphere2500", 5, 148, 1), ("sphere2500", 3, 37, 3), ("parking-garage", 5, 148, -1),
-                                            ("torus3D", 5, 148, -1), ("sphere2500", 5, 148, 0)])
+                                            ("torus3D", 5, 148, -1), ("sphere2500", 5, 148, 0),
+                                            # grids of the cluster launch mode (<= 16 CTAs interpret the whole plan)
+                                            ("smallGrid3D", 5, 2, -1), ("CSAIL", 3, 10, 2), ("parking-garage", 5, 16, 2)])
 def test_emulated_plan_matches_sparse_lu(ds, r, grid, cuts, data_dir):
     edges, n = pg.read_g2o_file(os.path.join(data_dir, ds + ".g2o"))
     brow, bcol, blocks = pg.connection_laplacian_blocks(edges)
