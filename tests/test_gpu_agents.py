@@ -16,7 +16,9 @@ def load(ds, data_dir):
 
 
 @pytest.mark.parametrize("ds,iters", [("smallGrid3D", 120), ("sphere2500", 50), ("torus3D", 30), ("CSAIL", 40), ("grid3D", 25),
-                                      ("parking-garage", 25)])
+                                      ("parking-garage", 25), ("rim", 20), ("ais2klinik", 20), ("city10000", 12), ("cubicle", 12),
+                                      ("input_INTEL_g2o", 20), ("input_M3500_g2o", 20), ("input_MITb_g2o", 20),
+                                      ("sphere_bignoise_vertex3", 15)])
 def test_greedy_schedule_reproduces_golden_trace(ds, iters, data_dir, golden_dir):
     from dpo_b200.agent import DistributedPGO
     edges, n = load(ds, data_dir)
@@ -29,7 +31,8 @@ def test_greedy_schedule_reproduces_golden_trace(ds, iters, data_dir, golden_dir
         gn.append(st.gradnorm)
     # parking-garage is ill-conditioned (kappa ~ 2, tau ~ 1: every tCG solve runs to its 10-iteration cap), so the
     # summation-order differences of the device-side G assembly are amplified above the print precision of the trace
-    ctol, gtol = (5e-8, 5e-6) if ds == "parking-garage" else (5e-9, 5e-8)
+    # (ais2klinik, SE(2), 15115 poses: the oracle itself sits 8e-9 from the printed trace, tests/test_oracle_golden.py)
+    ctol, gtol = (5e-8, 5e-6) if ds == "parking-garage" else ((2e-8, 5e-8) if ds == "ais2klinik" else (5e-9, 5e-8))
     assert np.max(np.abs(np.array(cost) - gold[:, 0]) / gold[:, 0]) <= ctol
     assert np.max(np.abs(np.array(gn) - gold[:, 1]) / gold[:, 1]) <= gtol
 

@@ -52,6 +52,23 @@ def test_grid3D_golden_trace(data_dir, golden_dir):
     assert np.max(np.abs(np.array(tr.gradnorm) - gold[:, 1]) / gold[:, 1]) <= 5e-9
 
 
+@pytest.mark.parametrize("ds,iters,tol", [("rim", 12, 5e-9), ("ais2klinik", 12, 2e-8), ("city10000", 10, 5e-9), ("cubicle", 10, 5e-9),
+                                          ("input_INTEL_g2o", 20, 5e-9), ("input_M3500_g2o", 20, 5e-9), ("input_MITb_g2o", 20, 5e-9),
+                                          ("sphere_bignoise_vertex3", 15, 5e-9)])
+def test_large_real_world_traces(ds, iters, tol, data_dir, golden_dir):
+    """Every other convergence trace the reference ships under result/graph/NP*.txt (5 agents): rim (SE(3), 10195 poses,
+    real scan), ais2klinik (SE(2), 15115 poses -- the largest 2-D one), city10000, cubicle, INTEL, M3500, MITb,
+    sphere_bignoise.  ais2klinik's first iterations sit 8e-9 from the printed values (the chordal initialisation of its
+    long odometry chains is ill-conditioned), hence 2e-8 there.  The kitti_* traces are at rounding-noise level (pure
+    odometry chains: the chordal initialisation is already optimal) and are not carried."""
+    meas, n = load(ds, data_dir)
+    drv = orc.MultiRobotDriver(meas, n, 5, r=5)
+    tr = drv.run(iters)
+    gold = np.loadtxt(os.path.join(golden_dir, f"NP{ds}_head400.txt"), delimiter=",")[:iters]
+    assert np.max(np.abs(np.array(tr.cost) - gold[:, 0]) / gold[:, 0]) <= tol
+    assert np.max(np.abs(np.array(tr.gradnorm) - gold[:, 1]) / gold[:, 1]) <= tol
+
+
 def test_final_trajectory_parking_garage(data_dir, golden_dir):
     """result/opt_pose/NPparking-garage.csv: X[:, :d]^T X after the reference's 1000-iteration
     5-agent run.  The run plateaus after ~400 iterations (every agent's local gradient norm is below the 1e-2 early
