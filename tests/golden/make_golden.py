@@ -21,7 +21,8 @@ LINES = 400
 OPT_POSE = ["parking-garage"]
 # graph-partition runs (examples/MultiRobotExample.cpp:76-91 reads graph/<robots>/<strength>/<dataset>, one agent id per line;
 # the matching trace is result/graph/<strength><dataset>.txt): (strength, dataset) pairs carried as fixtures
-PARTITIONED = [("strong", "CSAIL"), ("strong", "smallGrid3D"), ("strong", "sphere2500")]
+PARTITIONED = [("strong", "CSAIL"), ("strong", "smallGrid3D"), ("strong", "sphere2500"), ("eco", "sphere2500"), ("fast", "torus3D"),
+               ("strong", "torus3D"), ("strong", "parking-garage"), ("eco", "CSAIL"), ("fast", "rim"), ("strong", "city10000")]
 
 
 def main():

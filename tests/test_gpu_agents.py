@@ -37,23 +37,26 @@ def test_greedy_schedule_reproduces_golden_trace(ds, iters, data_dir, golden_dir
     assert np.max(np.abs(np.array(gn) - gold[:, 1]) / gold[:, 1]) <= gtol
 
 
-@pytest.mark.parametrize("ds,iters", [("CSAIL", 60), ("sphere2500", 40)])
-def test_partition_file_reproduces_golden_trace(ds, iters, data_dir, golden_dir):
-    """Non-contiguous ownership from the reference's partition files (graph/5/strong/<dataset>) through the device
-    runner: agents own scattered poses, public poses are most of them -- against result/graph/strong<dataset>.txt."""
+@pytest.mark.parametrize("strength,ds,iters", [("strong", "CSAIL", 60), ("strong", "sphere2500", 40), ("eco", "sphere2500", 20),
+                                               ("fast", "torus3D", 15), ("strong", "torus3D", 15), ("strong", "parking-garage", 12),
+                                               ("eco", "CSAIL", 30), ("fast", "rim", 10), ("strong", "city10000", 10)])
+def test_partition_file_reproduces_golden_trace(strength, ds, iters, data_dir, golden_dir):
+    """Non-contiguous ownership from the reference's partition files (graph/5/<strength>/<dataset>, KaHIP presets) through
+    the device runner: agents own scattered poses -- against result/graph/<strength><dataset>.txt."""
     from dpo_b200.agent import DistributedPGO
     from dpo_b200 import posegraph as pg
     edges, n = load(ds, data_dir)
-    owner = pg.read_partition_file(os.path.join(golden_dir, f"partition5_strong_{ds}.txt"), n)
+    owner = pg.read_partition_file(os.path.join(golden_dir, f"partition5_{strength}_{ds}.txt"), n)
     run = DistributedPGO(edges, n, 5, r=5, schedule="greedy", owner=owner)
-    gold = np.loadtxt(os.path.join(golden_dir, f"strong{ds}_head400.txt"), delimiter=",")[:iters]
+    gold = np.loadtxt(os.path.join(golden_dir, f"{strength}{ds}_head400.txt"), delimiter=",")[:iters]
     cost, gn = [], []
     for _ in range(iters):
         st = run.step()
         cost.append(st.cost)
         gn.append(st.gradnorm)
-    assert np.max(np.abs(np.array(cost) - gold[:, 0]) / gold[:, 0]) <= 5e-9
-    assert np.max(np.abs(np.array(gn) - gold[:, 1]) / gold[:, 1]) <= 5e-8
+    ctol, gtol = (5e-8, 5e-6) if ds == "parking-garage" else (5e-9, 5e-8)
+    assert np.max(np.abs(np.array(cost) - gold[:, 0]) / gold[:, 0]) <= ctol
+    assert np.max(np.abs(np.array(gn) - gold[:, 1]) / gold[:, 1]) <= gtol
 
 
 @pytest.mark.parametrize("ds,k,rounds,conc", [("torus3D", 8, 10, False), ("parking-garage", 4, 8, False), ("sphere2500", 8, 8, False),

@@ -99,15 +99,18 @@ def test_coloured_schedule_is_sequential_rbcd(data_dir):
     assert all(np.diff(a.trace.cost) <= 1e-9)
 
 
-@pytest.mark.parametrize("ds,iters", [("CSAIL", 60), ("smallGrid3D", 60), ("sphere2500", 30)])
-def test_partition_file_traces(ds, iters, data_dir, golden_dir):
-    """Graph-partition runs (ref examples/MultiRobotExample.cpp:76-91): agent ids from graph/5/strong/<dataset>, trace
-    result/graph/strong<dataset>.txt (partition ingestion)."""
+@pytest.mark.parametrize("strength,ds,iters", [("strong", "CSAIL", 60), ("strong", "smallGrid3D", 60), ("strong", "sphere2500", 30),
+                                               ("eco", "sphere2500", 12), ("fast", "torus3D", 12), ("strong", "torus3D", 12),
+                                               ("strong", "parking-garage", 12), ("eco", "CSAIL", 30), ("fast", "rim", 8),
+                                               ("strong", "city10000", 10)])
+def test_partition_file_traces(strength, ds, iters, data_dir, golden_dir):
+    """Graph-partition runs (ref examples/MultiRobotExample.cpp:76-91): agent ids from graph/5/<strength>/<dataset> (KaHIP
+    presets strong / eco / fast), trace result/graph/<strength><dataset>.txt (partition ingestion)."""
     meas, n = load(ds, data_dir)
-    owner = np.loadtxt(os.path.join(golden_dir, f"partition5_strong_{ds}.txt"), dtype=np.int64)
+    owner = np.loadtxt(os.path.join(golden_dir, f"partition5_{strength}_{ds}.txt"), dtype=np.int64)
     drv = orc.MultiRobotDriver(meas, n, 5, r=5, owner=owner)
     tr = drv.run(iters)
-    gold = np.loadtxt(os.path.join(golden_dir, f"strong{ds}_head400.txt"), delimiter=",")[:iters]
+    gold = np.loadtxt(os.path.join(golden_dir, f"{strength}{ds}_head400.txt"), delimiter=",")[:iters]
     assert np.max(np.abs(np.array(tr.cost) - gold[:, 0]) / gold[:, 0]) <= 5e-9
     assert np.max(np.abs(np.array(tr.gradnorm) - gold[:, 1]) / gold[:, 1]) <= 5e-9
 
