@@ -144,7 +144,8 @@ def cpu_reference_steps(steps: int, warmup: int, sample_desc_only: bool = False)
             pass
         kind, cores = "port", best
         label = ("C++ restatement of the reference path (scalar-CSR X*Q, min-degree sparse LDL^T solves of Q+0.1I, "
-                 "ROPTLIB RTR/tCG restated; 10+j products per call), g++ -O3")
+                 "ROPTLIB RTR/tCG restated; 10+j products per call), g++ -O3.  The reference itself cannot be built here (Eigen / "
+                 "SuiteSparse / ROPTLIB absent); its CHOLMOD supernodal factor solves are plausibly 2-4x faster than this port's")
     else:
         prob = orc.QuadraticProblem(n, meas.d, RANK_R)
         prob.set_Q(Q)
