@@ -476,11 +476,12 @@ int build_from_triplets(dpgo_problem *p, std::vector<BlockTriplet> &trip, unsign
   int grid = p->max_grid;
   const bool dense = (precond_mask & ((1u << DPGO_PRECOND_DENSE_EXACT) | (1u << DPGO_PRECOND_SPARSE_EXACT))) != 0;
   if (!dense) grid = std::max(1, std::min(grid, (n + rows_per_pass - 1) / rows_per_pass));
-  // Opt-in experiment (DPGO_CLUSTER_MAX_POSES=<n>, default off): agents of up to n poses run as ONE thread-block cluster
-  // (<= 16 CTAs) whose phase ends are hardware cluster barriers instead of the atomic-counter grid barrier.  Measured on B200
-  // (scripts/phase_times.py --agents 8 / 16, sphere2500): SLOWER than the full grid -- 0.259 vs 0.144 ms per step at 312 poses,
-  // 0.176 vs 0.138 ms at 156 poses: the barrier is cheaper, but 10-16 SMs stream the preconditioner blocks (12.5 / 3.1 MB per
-  // application) 2.5x slower than 148 SMs and every warp walks several rows per sparse phase.
+  // Launch mode 1 (dpgo_problem_set_launch_mode; or DPGO_CLUSTER_MAX_POSES=<n> for handles left at the default): the step
+  // kernel runs as ONE thread-block cluster (<= 16 CTAs) whose phase ends are hardware cluster barriers instead of the
+  // atomic-counter grid barrier.  For one agent alone this is SLOWER than the full grid (scripts/phase_times.py --agents 8 /
+  // 16, sphere2500: 0.259 vs 0.144 ms per step at 312 poses, 0.176 vs 0.138 ms at 156 poses: 10-16 SMs stream the
+  // preconditioner blocks 2.5x slower than 148 SMs); its point is that a cluster launch is not cooperative, so the agents of
+  // a colour class run side by side on one GPU and the round captures into a CUDA graph (dpgo_agents_round_async).
   static const int cluster_max_poses = [] { const char *e = std::getenv("DPGO_CLUSTER_MAX_POSES"); return e ? std::atoi(e) : 0; }();
   p->cluster = false;
   const bool want_cluster = p->launch_mode == 1 || (p->launch_mode < 0 && n <= cluster_max_poses);
