@@ -375,6 +375,52 @@ def synthetic_grid_graph(nx: int, ny: int, nz: int, edges_per_pose: float = 4.0,
     return edges, n, Tgt
 
 
+def grid_lattice_coords(nx: int, ny: int, nz: int) -> np.ndarray:
+    """(n, 3) lattice coordinates of the poses of synthetic_grid_graph (ids follow the boustrophedon path)."""
+    n = nx * ny * nz
+    coords = np.zeros((n, 3), dtype=np.int64)
+    k = 0
+    row = 0
+    for z in range(nz):
+        ys = range(ny) if z % 2 == 0 else range(ny - 1, -1, -1)
+        for y in ys:
+            xs = np.arange(nx) if row % 2 == 0 else np.arange(nx - 1, -1, -1)
+            coords[k:k + nx, 0] = xs
+            coords[k:k + nx, 1] = y
+            coords[k:k + nx, 2] = z
+            k += nx
+            row += 1
+    return coords
+
+
+def grid_block_owner(nx: int, ny: int, nz: int, k: int) -> np.ndarray:
+    """Pose -> agent for the synthetic lattice: k = kx*ky*kz rectangular blocks with the smallest total cut surface
+    (BASELINE config 5 with 8 agents: 2 x 2 x 2 blocks).  The contiguous id ranges of examples/MultiRobotExample.cpp:95-109
+    cut a 100 x 100 x 10 lattice into 1.25-layer slabs in which EVERY pose is public; blocks keep the public poses at the
+    block faces.  Use as DistributedPGO(..., owner=grid_block_owner(...))."""
+    best = None
+    for kx in range(1, k + 1):
+        if k % kx:
+            continue
+        for ky in range(1, k // kx + 1):
+            if (k // kx) % ky:
+                continue
+            kz = k // (kx * ky)
+            if kx > nx or ky > ny or kz > nz:
+                continue
+            cut = (kx - 1) * ny * nz + (ky - 1) * nx * nz + (kz - 1) * nx * ny
+            if best is None or cut < best[0]:
+                best = (cut, kx, ky, kz)
+    if best is None:
+        raise ValueError(f"cannot cut a {nx}x{ny}x{nz} lattice into {k} blocks")
+    _, kx, ky, kz = best
+    c = grid_lattice_coords(nx, ny, nz)
+    bx = np.minimum(c[:, 0] * kx // nx, kx - 1)
+    by = np.minimum(c[:, 1] * ky // ny, ky - 1)
+    bz = np.minimum(c[:, 2] * kz // nz, kz - 1)
+    return ((bz * ky + by) * kx + bx).astype(np.int64)
+
+
 def read_partition_file(path: str, n: int | None = None) -> np.ndarray:
     """Pose -> agent map from a graph-partition file, one agent id per line in pose order
     (ref examples/MultiRobotExample.cpp:76-91: graph/<robots>/<strength>/<dataset>)."""

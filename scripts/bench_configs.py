@@ -37,6 +37,9 @@ def main():
     ap.add_argument("--stop", type=float, default=0.1)
     ap.add_argument("--max-rounds", type=int, default=3000)
     ap.add_argument("--grid", default="100,100,10", help="synthetic grid dims when --dataset synthetic")
+    ap.add_argument("--partition", default="blocks", choices=["blocks", "ranges"],
+                    help="synthetic grid: kx*ky*kz lattice blocks (public poses only at the block faces) or the reference's "
+                         "contiguous id ranges (1.25-layer slabs: every pose public)")
     args = ap.parse_args()
 
     import torch
@@ -62,19 +65,21 @@ def main():
         rng = np.random.default_rng(1)
         T0 = Tgt.copy()
         T0.reshape(3, n, 4)[:, :, 3] += 0.3 * rng.standard_normal((3, n))
-        label = f"synthetic grid {dims} = {n} poses / {len(edges)} edges"
+        label = f"synthetic grid {dims} = {n} poses / {len(edges)} edges, partition {args.partition}"
+        owner = pg.grid_block_owner(*dims, args.agents) if args.partition == "blocks" else None
     else:
         edges, n = pg.read_g2o_file(os.path.join(ROOT, "data", args.dataset + ".g2o"))
         T0 = pg.chordalInitialization(edges.d, n, edges)
         label = f"{args.dataset}.g2o = {n} poses / {len(edges)} edges"
+        owner = None
     r = 5
     X0 = pg.fixedStiefelVariable(edges.d, r) @ T0
-    precond = dp.PRECOND_DENSE_EXACT if args.precond == "exact" else dp.PRECOND_BLOCK_JACOBI
+    precond = dp.PRECOND_SPARSE_EXACT if args.precond == "exact" else dp.PRECOND_BLOCK_JACOBI
     alg = dp.ROPTALG.RTR if args.alg == "rtr" else dp.ROPTALG.RGD
 
     def make():
         return DistributedPGO(edges, n, args.agents, r=r, algorithm=alg, preconditioner=precond, schedule=args.schedule,
-                              X_init=X0, rank=rank, world=world, device=local_rank, dist=dist)
+                              X_init=X0, rank=rank, world=world, device=local_rank, dist=dist, owner=owner)
 
     def barrier():
         if world > 1:

@@ -52,3 +52,25 @@ def test_synthetic_grid():
     m = orc.Measurements(3, e.r1, e.r2, e.p1, e.p2, e.R, e.t, e.kappa, e.tau, e.weight)
     p.set_Q(orc.construct_connection_laplacian(m, n))
     assert 2 * p.f(Tgt) / len(e) < 200 * 3 * 0.05 ** 2 * 4 + 100 * 3 * 0.1 ** 2 * 2
+
+
+def test_block_partition_of_the_synthetic_lattice():
+    """BASELINE config 5 hygiene: 8 agents as 2 x 2 x 2 blocks of the lattice instead of contiguous id ranges (slabs in
+    which every pose is public): far fewer public poses, balanced blocks, a valid owner map for the exchange plan."""
+    from dpo_b200.agent import ExchangePlan, contiguous_owner, partition_edges
+    nx, ny, nz, k = 20, 20, 8, 8
+    e, n, _ = pg.synthetic_grid_graph(nx, ny, nz, edges_per_pose=4.0, seed=0)
+    c = pg.grid_lattice_coords(nx, ny, nz)
+    assert c.shape == (n, 3) and np.abs(np.diff(c, axis=0)).sum(axis=1).max() == 1     # the id path visits lattice neighbours
+    owner = pg.grid_block_owner(nx, ny, nz, k)
+    assert owner.shape == (n,) and set(owner.tolist()) == set(range(k))
+    assert np.bincount(owner).min() == np.bincount(owner).max() == n // k
+    pub = {}
+    for name, own in (("blocks", owner), ("ranges", contiguous_owner(n, k))):
+        parts, counts, glob = partition_edges(e, own, k)
+        plan = ExchangePlan([p[2] for p in parts], k)
+        pub[name] = sum(len(q) for q in plan.public)
+    assert pub["ranges"] == n                       # slabs: every pose is public
+    assert pub["blocks"] < 0.7 * pub["ranges"]     # (random closures reach 3 lattice steps across a block face)
+    with pytest.raises(ValueError):
+        pg.grid_block_owner(2, 2, 2, 16)
